@@ -1,0 +1,44 @@
+// Library-level entry points of the C ABI: versioning, thread-local error string, device info.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "../../include/dasp_b200.h"
+
+namespace dasp {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int sm_count() {
+  static thread_local int cached_dev = -1;
+  static thread_local int cached_sms = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached_dev = dev;
+    cached_sms = n;
+  }
+  return cached_sms;
+}
+
+void reverb_shutdown();  // reverb.cu
+
+}  // namespace dasp
+
+extern "C" {
+
+int dasp_abi_version(void) { return DASP_ABI_VERSION; }
+const char* dasp_last_error(void) { return dasp::g_err; }
+int dasp_compiled_arch(void) { return 1000; }
+void dasp_shutdown(void) { dasp::reverb_shutdown(); }
+
+}  // extern "C"

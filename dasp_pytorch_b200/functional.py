@@ -1,0 +1,267 @@
+"""B200-native drop-in for ``dasp_pytorch.functional``'s audio-processor hot path.
+
+Same function names, argument order, keyword names, defaults and
+``(batch, channels, samples)`` tensor contract as the reference
+(``dasp_pytorch/functional.py`` @ c9ae0126), so that
+``Processor.process_normalized`` -> ``process_fn(x, sample_rate, **params)``
+(reference ``modules.py:45-49``) and direct calls keep working unchanged.  Every
+op is a ``torch.autograd.Function`` whose forward and backward call hand-written
+sm_100a kernels through the C ABI in ``include/dasp_b200.h``; there is no PyTorch,
+Triton or CPU fallback -- non-CUDA inputs raise ``DaspError``.
+
+Arithmetic is fp32 (coefficient design in fp64 inside the kernels).  Inputs in
+another floating dtype are computed in fp32 and returned in the input dtype.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from dasp_pytorch_b200 import _abi
+from dasp_pytorch_b200._abi import DaspError, check, ptr, stream_ptr
+
+__all__ = [
+    "gain",
+    "distortion",
+    "parametric_eq",
+    "compressor",
+    "expander",
+    "noise_shaped_reverberation",
+]
+
+
+# --------------------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------------------
+
+
+def _audio(x: torch.Tensor, name: str = "x"):
+    """validate the (bs, chs, n) audio tensor -> (fp32 contiguous tensor, original dtype)"""
+    if not torch.is_tensor(x) or x.dim() != 3:
+        raise ValueError(f"{name} must be a tensor of shape (batch, channels, samples)")
+    if not x.is_cuda:
+        raise DaspError(
+            f"{name} is on {x.device}: dasp_pytorch_b200 only runs on CUDA (B200) tensors and has no CPU path"
+        )
+    if not x.is_floating_point():
+        raise DaspError(f"{name} must be a floating-point tensor, got {x.dtype}")
+    return x.to(torch.float32).contiguous(), x.dtype
+
+
+def _param(p, n_expected: int, like: torch.Tensor, name: str, allow_broadcast: bool = False) -> torch.Tensor:
+    """flatten a parameter to fp32 ``(n_expected,)`` on x's device, keeping autograd history.
+
+    The reference reshapes parameters with ``.view(bs, 1, 1)`` and friends, i.e. it accepts
+    any shape holding the right number of elements; integer tensors are
+    promoted (examples/demo.py:44 passes int64 cut-offs).
+    """
+    if not torch.is_tensor(p):
+        p = torch.as_tensor(p)
+    if p.device != like.device:
+        if p.numel() == 1 and not p.requires_grad:
+            p = p.to(like.device)
+        else:
+            raise DaspError(f"{name} is on {p.device} but x is on {like.device}")
+    p = p.reshape(-1).to(torch.float32)
+    if p.numel() != n_expected:
+        if allow_broadcast and p.numel() == 1:
+            p = p.expand(n_expected)
+        else:
+            raise RuntimeError(
+                f"{name}: expected {n_expected} element(s) (one per batch item), got {p.numel()}"
+            )
+    return p
+
+
+def _ws(n_floats: int, device) -> torch.Tensor:
+    return torch.empty(max(int(n_floats), 1), dtype=torch.float32, device=device)
+
+
+# --------------------------------------------------------------------------------------
+# gain / distortion
+# --------------------------------------------------------------------------------------
+
+
+class _PointwiseFn(torch.autograd.Function):
+    """y = f(x * 10^(p_db/20)) with one p_db per row; f = identity (gain) or tanh (distortion)."""
+
+    @staticmethod
+    def forward(ctx, x, p_db, kind: str, rows: int, n: int):
+        lib = _abi.lib()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            st = stream_ptr(x.device)
+            if kind == "gain":
+                check(lib.dasp_gain_fwd(ptr(x), ptr(p_db), ptr(y), rows, 1, n, st), "dasp_gain_fwd")
+            else:
+                check(lib.dasp_distortion_fwd(ptr(x), ptr(p_db), ptr(y), rows, n, st), "dasp_distortion_fwd")
+        ctx.save_for_backward(x, p_db)
+        ctx.kind, ctx.rows, ctx.n = kind, rows, n
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _abi.lib()
+        x, p_db = ctx.saved_tensors
+        rows, n = ctx.rows, ctx.n
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        gp = torch.empty_like(p_db)
+        nws = lib.dasp_pointwise_bwd_workspace_floats(rows, n)
+        ws = _ws(nws, x.device)
+        with torch.cuda.device(x.device):
+            st = stream_ptr(x.device)
+            if ctx.kind == "gain":
+                check(lib.dasp_gain_bwd(ptr(gy), ptr(x), ptr(p_db), ptr(gx), ptr(gp), ptr(ws), nws, rows, 1, n, st),
+                      "dasp_gain_bwd")
+            else:
+                check(lib.dasp_distortion_bwd(ptr(gy), ptr(x), ptr(p_db), ptr(gx), ptr(gp), ptr(ws), nws, rows, n,
+                                              st), "dasp_distortion_bwd")
+        return gx, gp, None, None, None
+
+
+def gain(x: torch.Tensor, sample_rate: int, gain_db: torch.Tensor):
+    """Apply a per-item gain in dB (reference ``functional.py:10-29``).
+
+    Args:
+        x: audio ``(bs, chs, seq_len)``.
+        sample_rate: unused (kept for the common processor signature).
+        gain_db: ``bs`` elements, any shape.
+    """
+    xf, dt = _audio(x)
+    bs, chs, n = xf.shape
+    g = _param(gain_db, bs, xf, "gain_db")
+    y = _PointwiseFn.apply(xf, g.contiguous(), "gain", bs, chs * n)
+    return y.to(dt)
+
+
+def distortion(x: torch.Tensor, sample_rate: int, drive_db: torch.Tensor):
+    """tanh soft clipper with drive in dB (reference ``functional.py:65-78``).
+
+    Like the reference's ``drive_db.view(bs, chs, -1)``, the drive needs one element per
+    (item, channel) row -- i.e. ``bs`` elements for mono input, ``bs*chs`` for multichannel.
+    """
+    xf, dt = _audio(x)
+    bs, chs, n = xf.shape
+    d = _param(drive_db, bs * chs, xf, "drive_db")
+    y = _PointwiseFn.apply(xf, d.contiguous(), "distortion", bs * chs, n)
+    return y.to(dt)
+
+
+# --------------------------------------------------------------------------------------
+# compressor / expander
+# --------------------------------------------------------------------------------------
+
+
+class _DynamicsFn(torch.autograd.Function):
+    """Feed-forward dynamics processor: kind 0 = compressor, 1 = expander."""
+
+    @staticmethod
+    def forward(ctx, x, threshold, ratio, attack, knee, makeup, kind, sample_rate, eps, lookahead):
+        lib = _abi.lib()
+        bs, chs, n = x.shape
+        y = torch.empty_like(x)
+        need_bwd = any(ctx.needs_input_grad[:6])
+        ckpt = None
+        with torch.cuda.device(x.device):
+            if need_bwd:
+                tile = lib.dasp_dynamics_tile_len(bs, chs)     # depends on the device's SM count
+                if tile <= 0:
+                    raise DaspError(f"dynamics: unsupported channel count {chs}")
+                ckpt = torch.empty(bs * max(1, -(-n // tile)), dtype=torch.float32, device=x.device)
+            check(lib.dasp_dynamics_fwd(kind, ptr(x), ptr(threshold), ptr(ratio), ptr(attack), ptr(knee),
+                                        ptr(makeup), ptr(y), ptr(ckpt), bs, chs, n, float(sample_rate),
+                                        float(eps), int(lookahead), stream_ptr(x.device)), "dasp_dynamics_fwd")
+        if need_bwd:
+            ctx.save_for_backward(x, threshold, ratio, attack, knee, makeup, ckpt)
+        ctx.cfg = (kind, float(sample_rate), float(eps), int(lookahead))
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _abi.lib()
+        x, threshold, ratio, attack, knee, makeup, ckpt = ctx.saved_tensors
+        kind, sample_rate, eps, lookahead = ctx.cfg
+        bs, chs, n = x.shape
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        gp = torch.empty(bs, 6, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(bs * n, dtype=torch.float32, device=x.device) if lookahead > 0 else None
+        with torch.cuda.device(x.device):
+            check(lib.dasp_dynamics_bwd(kind, ptr(gy), ptr(x), ptr(threshold), ptr(ratio), ptr(attack), ptr(knee),
+                                        ptr(makeup), ptr(ckpt), ptr(gx), ptr(gp), ptr(scratch), bs, chs, n,
+                                        sample_rate, eps, lookahead, stream_ptr(x.device)), "dasp_dynamics_bwd")
+        return gx, gp[:, 0], gp[:, 1], gp[:, 2], gp[:, 4], gp[:, 5], None, None, None, None
+
+
+def _dynamics(kind, x, sample_rate, threshold_db, ratio, attack_ms, release_ms, knee_db, makeup_gain_db, eps,
+              lookahead_samples):
+    xf, dt = _audio(x)
+    bs = xf.shape[0]
+    ps = [
+        _param(p, bs, xf, name, allow_broadcast=True).contiguous()
+        for p, name in (
+            (threshold_db, "threshold_db"),
+            (ratio, "ratio"),
+            (attack_ms, "attack_ms"),
+            (knee_db, "knee_db"),
+            (makeup_gain_db, "makeup_gain_db"),
+        )
+    ]
+    # release_ms is validated for shape only: the reference accepts and ignores it
+    # (functional.py:333,343-344), so it receives no gradient here either.
+    _param(release_ms, bs, xf, "release_ms", allow_broadcast=True)
+    y = _DynamicsFn.apply(xf, *ps, kind, sample_rate, eps, int(lookahead_samples))
+    return y.to(dt)
+
+
+def compressor(
+    x: torch.Tensor,
+    sample_rate: float,
+    threshold_db: torch.Tensor,
+    ratio: torch.Tensor,
+    attack_ms: torch.Tensor,
+    release_ms: torch.Tensor,
+    knee_db: torch.Tensor,
+    makeup_gain_db: torch.Tensor,
+    eps: float = 1e-8,
+    lookahead_samples: int = 0,
+):
+    """Feed-forward dynamic range compressor (reference ``functional.py:275-399``).
+
+    Side chain = sum of the channels, soft-knee static curve, one-pole *attack* smoothing of the
+    gain-reduction curve (``release_ms`` is accepted and ignored exactly like the reference),
+    makeup gain, optional look-ahead delay of the audio path.  The smoother is evaluated as
+    the true zero-state recursion; the reference's frequency-sampling evaluation is identical
+    up to the time-aliased tail of the smoother's impulse response.
+    """
+    return _dynamics(0, x, sample_rate, threshold_db, ratio, attack_ms, release_ms, knee_db, makeup_gain_db, eps,
+                     lookahead_samples)
+
+
+def expander(
+    x: torch.Tensor,
+    sample_rate: float,
+    threshold_db: torch.Tensor,
+    ratio: torch.Tensor,
+    attack_ms: torch.Tensor,
+    release_ms: torch.Tensor,
+    knee_db: torch.Tensor,
+    makeup_gain_db: torch.Tensor,
+    eps: float = 1e-8,
+    lookahead_samples: int = 0,
+):
+    """Downward expander with the compressor's signature.
+
+    The reference only stubs this op (``functional.py:402-403`` raises
+    ``NotImplementedError``), so there is no reference parity to claim: the static curve is the
+    soft-knee downward expander of Giannoulis et al. (2012) -- gain ``(R-1)(x_dB-T)`` below the
+    knee, quadratic knee of width ``knee_db``, unity above -- followed by the compressor's
+    attack smoother and makeup gain.  Pinned to ``oracle.expander``.
+    """
+    return _dynamics(1, x, sample_rate, threshold_db, ratio, attack_ms, release_ms, knee_db, makeup_gain_db, eps,
+                     lookahead_samples)
+
+
+# the remaining processors are appended below as their kernels land

@@ -1,0 +1,83 @@
+/* dasp_b200.h -- C ABI of libdasp_b200.so: the B200 (sm_100a) kernels behind
+ * dasp_pytorch.functional's batched audio-processor hot path.
+ *
+ * The reference (csteinmetz1/dasp-pytorch @ c9ae0126) is pure Python and has no FFI of its
+ * own; each entry point below replaces the arithmetic of one reference function and is what
+ * a ctypes/cffi binding inside that function would call (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (unless stated), owned by the
+ *     caller; the library never allocates tensors -- scratch comes in through `ws`
+ *     arguments sized by the matching *_workspace_* query;
+ *   - audio tensors are (batch, channels, samples) row-major, exactly the reference's
+ *     tensor contract (README.md:38);
+ *   - `stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises;
+ *   - return value 0 = ok, negative = error (see DASP_ERR_*); the message is available
+ *     from dasp_last_error() (thread-local).  No exception crosses this boundary;
+ *   - reentrant from several host threads as long as they use distinct streams.
+ */
+#ifndef DASP_B200_H_
+#define DASP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DASP_ABI_VERSION 1
+
+#define DASP_OK 0
+#define DASP_ERR_INVALID (-1)   /* bad shape / null pointer / misalignment        */
+#define DASP_ERR_CUDA (-2)      /* CUDA runtime call or kernel launch failed      */
+#define DASP_ERR_CUFFT (-3)     /* cuFFT call failed                              */
+#define DASP_ERR_WORKSPACE (-4) /* caller workspace smaller than *_workspace_*()  */
+
+/* ---- library ---------------------------------------------------------------------- */
+int dasp_abi_version(void);
+const char* dasp_last_error(void);
+/* compiled-for architecture as an integer (1000 for sm_100a) */
+int dasp_compiled_arch(void);
+/* frees cached cuFFT plans and device-side filter-bank spectra */
+void dasp_shutdown(void);
+
+/* ---- gain: y = x * 10^(gain_db/20)            (reference functional.py:10-29) ------ */
+int dasp_gain_fwd(const float* x, const float* gain_db /* [bs] */, float* y, int64_t bs, int64_t chs,
+                  int64_t n, void* stream);
+int dasp_gain_bwd(const float* gy, const float* x, const float* gain_db, float* gx,
+                  float* g_gain_db /* [bs] */, float* ws, int64_t ws_floats, int64_t bs, int64_t chs,
+                  int64_t n, void* stream);
+
+/* ---- distortion: y = tanh(x * 10^(drive_db/20))   (reference functional.py:65-78) --
+ * rows = bs*chs; one drive value per row (the reference's drive_db.view(bs, chs, -1)). */
+int dasp_distortion_fwd(const float* x, const float* drive_db /* [rows] */, float* y, int64_t rows,
+                        int64_t n, void* stream);
+int dasp_distortion_bwd(const float* gy, const float* x, const float* drive_db, float* gx,
+                        float* g_drive_db /* [rows] */, float* ws, int64_t ws_floats, int64_t rows,
+                        int64_t n, void* stream);
+/* floats of scratch the two *_bwd calls above need (rows = bs for gain with n = chs*N) */
+int64_t dasp_pointwise_bwd_workspace_floats(int64_t rows, int64_t n);
+
+/* ---- compressor / expander            (reference functional.py:275-399; :402-403 stub) --
+ * kind: 0 = compressor (reference semantics: attack-only smoothing, release_ms unused),
+ *       1 = downward expander (new op, same signature; the reference only stubs it).
+ * Parameters are [bs] arrays.  `ckpt` (fwd: optional out, bwd: in) holds the smoother state at
+ * every tile boundary: bs * ceil(n / dasp_dynamics_tile_len(bs, chs)) floats; pass NULL in the
+ * forward when no backward will follow.  gparams is [bs][6] in signature order
+ * (threshold, ratio, attack, release(=0), knee, makeup).  g_scratch (bs*n floats) is only
+ * needed when lookahead > 0. */
+int64_t dasp_dynamics_tile_len(int64_t bs, int64_t chs);
+int dasp_dynamics_fwd(int kind, const float* x, const float* threshold_db, const float* ratio,
+                      const float* attack_ms, const float* knee_db, const float* makeup_db, float* y,
+                      float* ckpt, int64_t bs, int64_t chs, int64_t n, float sample_rate, float eps,
+                      int64_t lookahead, void* stream);
+int dasp_dynamics_bwd(int kind, const float* gy, const float* x, const float* threshold_db,
+                      const float* ratio, const float* attack_ms, const float* knee_db,
+                      const float* makeup_db, const float* ckpt, float* gx, float* gparams,
+                      float* g_scratch, int64_t bs, int64_t chs, int64_t n, float sample_rate, float eps,
+                      int64_t lookahead, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DASP_B200_H_ */

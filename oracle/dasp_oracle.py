@@ -116,19 +116,28 @@ def eq_sections(sample_rate, params):
     return torch.stack(rows, dim=1)
 
 
-def _fsm_size(n: int) -> int:
-    """FFT size of the frequency-sampling method: 2^ceil(log2(2n-1)) (signal.py:109,150)."""
-    return 1 << max(0, math.ceil(math.log2(max(1, 2 * n - 1))))
+def _fsm_size(n: int, tail: int = 0) -> int:
+    """FFT size of the frequency-sampling method: 2^ceil(log2(2n-1)) (signal.py:109,150).
+
+    ``tail`` > 0 is a test-only extension: enlarge the grid to at least ``n + tail`` points so
+    that an impulse response up to ``tail`` samples long does not wrap around (the reference's
+    own grid leaves ``n_fft - n`` samples, which time-aliases long decays at small ``n``).
+    With a large tail the result is the true zero-state IIR *and* stays differentiable.
+    """
+    size = 1 << max(0, math.ceil(math.log2(max(1, 2 * n - 1))))
+    if tail > 0:
+        size = max(size, 1 << math.ceil(math.log2(n + tail)))
+    return size
 
 
-def sos_frequency_sampling(sos: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+def sos_frequency_sampling(sos: torch.Tensor, x: torch.Tensor, tail: int = 0) -> torch.Tensor:
     """Cascade filtering the way the reference does it: sample H on an FFT grid.
 
     H = prod_k rfft(b_k, n)/rfft(a_k, n) (signal.py:7-11, 14-32), one response per
     batch item shared by all channels (signal.py:157-158), then
     irfft(rfft(x, n) * H)[..., :N] (signal.py:35-39, 161-164).
     """
-    n = _fsm_size(x.shape[-1])
+    n = _fsm_size(x.shape[-1], tail)
     resp = None
     for k in range(sos.shape[1]):
         hk = torch.fft.rfft(sos[:, k, :3], n) / torch.fft.rfft(sos[:, k, 3:], n)
@@ -153,7 +162,7 @@ def sos_recursion_truth(sos: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
     return torch.from_numpy(out)
 
 
-def parametric_eq(x: torch.Tensor, sample_rate, *params, method: str = "fsm") -> torch.Tensor:
+def parametric_eq(x: torch.Tensor, sample_rate, *params, method: str = "fsm", fsm_tail: int = 0) -> torch.Tensor:
     """Six-section parametric EQ (functional.py:118-272).
 
     ``params``: the 18 tensors of the reference signature, any shape with ``bs``
@@ -167,7 +176,7 @@ def parametric_eq(x: torch.Tensor, sample_rate, *params, method: str = "fsm") ->
     if method == "recursion":
         return sos_recursion_truth(sos, x).to(x.dtype)
     sos = sos.to(x.dtype) if not sos.is_floating_point() else sos
-    return sos_frequency_sampling(sos.type_as(x), x)
+    return sos_frequency_sampling(sos.type_as(x), x, fsm_tail)
 
 
 # --------------------------------------------------------------------------------------
@@ -180,7 +189,7 @@ def _attack_coefficient(attack_ms, sample_rate):
     return torch.exp(-math.log(9.0) / (sample_rate * (attack_ms / 1e3)))
 
 
-def _one_pole_fsm(gc: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
+def _one_pole_fsm(gc: torch.Tensor, alpha: torch.Tensor, tail: int = 0) -> torch.Tensor:
     """s[n] = alpha s[n-1] + (1-alpha) gc[n] by frequency sampling.
 
     b = [1-alpha, 0], a = [1, -alpha] (functional.py:372-379) pushed through the
@@ -191,7 +200,7 @@ def _one_pole_fsm(gc: torch.Tensor, alpha: torch.Tensor) -> torch.Tensor:
     zero = torch.zeros_like(al)
     b = torch.cat([1.0 - al, zero], dim=-1)
     a = torch.cat([torch.ones_like(al), -al], dim=-1)
-    n = _fsm_size(gc.shape[-1])
+    n = _fsm_size(gc.shape[-1], tail)
     resp = (torch.fft.rfft(b, n) / torch.fft.rfft(a, n)).unsqueeze(1)
     return torch.fft.irfft(torch.fft.rfft(gc, n) * resp, n)[..., : gc.shape[-1]]
 
@@ -207,7 +216,7 @@ def one_pole_recursion_truth(gc: torch.Tensor, alpha: torch.Tensor) -> torch.Ten
 
 
 def _dynamics(x, sample_rate, threshold_db, ratio, attack_ms, knee_db, makeup_gain_db,
-              eps, lookahead_samples, curve, smoother):
+              eps, lookahead_samples, curve, smoother, fsm_tail=0):
     bs, chs, n = x.shape
     side = x.sum(dim=1, keepdim=True)                       # functional.py:328
     t = threshold_db.reshape(bs, 1, 1)
@@ -220,7 +229,7 @@ def _dynamics(x, sample_rate, threshold_db, ratio, attack_ms, knee_db, makeup_ga
     if smoother == "recursion":
         sm = one_pole_recursion_truth(gc, alpha).to(x.dtype)
     else:
-        sm = _one_pole_fsm(gc, alpha)                       # functional.py:380
+        sm = _one_pole_fsm(gc, alpha, fsm_tail)             # functional.py:380
     if lookahead_samples > 0:                               # functional.py:383-385
         delayed = torch.zeros_like(x)
         delayed[..., lookahead_samples:] = x[..., : n - lookahead_samples]
@@ -250,14 +259,14 @@ def _compressor_curve(level_db, t, r, w):
 
 def compressor(x, sample_rate, threshold_db, ratio, attack_ms, release_ms, knee_db,
                makeup_gain_db, eps: float = 1e-8, lookahead_samples: int = 0,
-               smoother: str = "fsm"):
+               smoother: str = "fsm", fsm_tail: int = 0):
     """Feed-forward compressor, attack-only smoothing (functional.py:275-399).
 
     ``release_ms`` is accepted and unused, exactly like the reference
     (functional.py:333,340,343-344); its gradient is None.
     """
     return _dynamics(x, sample_rate, threshold_db, ratio, attack_ms, knee_db, makeup_gain_db,
-                     eps, lookahead_samples, _compressor_curve, smoother)
+                     eps, lookahead_samples, _compressor_curve, smoother, fsm_tail)
 
 
 def _expander_curve(level_db, t, r, w):
@@ -281,10 +290,10 @@ def _expander_curve(level_db, t, r, w):
 
 def expander(x, sample_rate, threshold_db, ratio, attack_ms, release_ms, knee_db,
              makeup_gain_db, eps: float = 1e-8, lookahead_samples: int = 0,
-             smoother: str = "fsm"):
+             smoother: str = "fsm", fsm_tail: int = 0):
     """Downward expander with the compressor's signature and smoother (new op)."""
     return _dynamics(x, sample_rate, threshold_db, ratio, attack_ms, knee_db, makeup_gain_db,
-                     eps, lookahead_samples, _expander_curve, smoother)
+                     eps, lookahead_samples, _expander_curve, smoother, fsm_tail)
 
 
 # --------------------------------------------------------------------------------------

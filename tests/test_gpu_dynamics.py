@@ -1,0 +1,126 @@
+"""compressor / expander on the GPU through the C ABI vs the CPU oracle and the reference golden.
+
+Tolerance (north star): 1e-4 relative fp32, judged per item against the fp64 arbiter with the
+SURVEY.md 8c rule err(new) <= max(1e-4, err(ref fp32))."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+from helpers import COMP_RANGES, SR, denorm, param_grad_err, peak_err, run_with_grads
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _inputs(bs, chs, n, seed, attack_max01=1.0):
+    g = torch.Generator().manual_seed(seed)
+    level = torch.rand(bs, 1, 1, generator=g)
+    x = (torch.rand(bs, chs, n, generator=g) * 2 - 1) * level
+    p01 = torch.rand(bs, 6, generator=g)
+    p01[:, 4] = p01[:, 4].clamp(min=0.05)        # knee > 0 (W == 0 gives NaN grads in the reference too)
+    p01[:, 2] *= attack_max01
+    return x, p01
+
+
+def _check(cuda_device, fn_gpu, fn_orc, x, params, grads=True, extra=None):
+    extra = extra or {}
+    y, dx, dp = run_with_grads(lambda xx, p: fn_gpu(xx, SR, *p, **extra), x, params, torch.float32, cuda_device)
+    y64, dx64, dp64 = run_with_grads(lambda xx, p: fn_orc(xx, SR, *p, **extra), x, params, torch.float64, "cpu")
+    y32, dx32, dp32 = run_with_grads(lambda xx, p: fn_orc(xx, SR, *p, **extra), x, params, torch.float32, "cpu")
+    e, e32 = peak_err(y, y64), peak_err(y32, y64)
+    assert (e <= torch.clamp(e32, min=TOL)).all(), (e, e32)
+    if grads:
+        e, e32 = peak_err(dx, dx64), peak_err(dx32, dx64)
+        assert (e <= torch.clamp(e32, min=TOL)).all(), ("dx", e, e32)
+        assert dp[3] is None and dp64[3] is None                      # release_ms: no gradient
+        e, e32 = param_grad_err(dp, dp64), param_grad_err(dp32, dp64)
+        assert (e <= torch.clamp(e32, min=TOL)).all(), ("dparam", e, e32)
+
+
+def test_compressor_golden(cuda_device):
+    import dasp_pytorch_b200 as D
+    g = load_golden("compressor.npz")
+    names = [str(s) for s in g["names"]]
+    params = denorm(g["p01"], COMP_RANGES)
+    y, dx, dp = run_with_grads(lambda xx, p: D.compressor(xx, SR, *p), g["x"], params, torch.float32, cuda_device)
+    # item 0 has a 90 ms attack at N=4096: the reference time-aliases there (tests/test_oracle_golden.py)
+    assert peak_err(y, g["comp_y64"])[1:].max() < TOL
+    assert peak_err(dx, g["comp_dx64"])[1:].max() < TOL
+    ref = [None if n == "release_ms" else torch.as_tensor(g[f"comp_d_{n}"]) for n in names]
+    assert param_grad_err(dp, ref)[1:].max() < TOL
+    y7 = D.compressor(torch.as_tensor(g["x"]).to(cuda_device), SR, *[p.to(cuda_device) for p in params],
+                      lookahead_samples=7).cpu()
+    assert peak_err(y7, g["comp_la7_y64"])[1:].max() < TOL
+
+
+@pytest.mark.parametrize("bs,chs,n", [(8, 2, 48000), (3, 1, 48000), (2, 3, 20000)])
+def test_compressor_full_ranges_vs_oracle(cuda_device, bs, chs, n):
+    import dasp_pytorch_b200 as D
+    x, p01 = _inputs(bs, chs, n, seed=5)
+    _check(cuda_device, D.compressor, oracle.compressor, x, denorm(p01, COMP_RANGES))
+
+
+@pytest.mark.parametrize("bs,chs,n", [(2, 2, 4097), (3, 2, 100), (2, 1, 1), (2, 2, 224 * 8 + 4), (2400, 1, 512),
+                                      (700, 2, 1000), (1300, 2, 900)])
+def test_compressor_ragged_shapes(cuda_device, bs, chs, n):
+    """unaligned N (scalar path), N smaller than a tile, every warps-per-item variant.  At these
+    small N the reference's FFT grid time-aliases the smoother tail, so the arbiter here is the
+    oracle with an enlarged grid (fsm_tail: alias-free == true recursion, still differentiable)."""
+    import dasp_pytorch_b200 as D
+    x, p01 = _inputs(bs, chs, n, seed=6)
+    params = denorm(p01, COMP_RANGES)
+    y, dx, dp = run_with_grads(lambda xx, p: D.compressor(xx, SR, *p), x, params, torch.float32, cuda_device)
+    y64, dx64, dp64 = run_with_grads(lambda xx, p: oracle.compressor(xx, SR, *p, fsm_tail=1 << 17), x, params,
+                                     torch.float64, "cpu")
+    yt = oracle.compressor(x.double(), SR, *[p.double() for p in params], smoother="recursion")
+    assert (peak_err(y64, yt) < 1e-9).all()          # enlarged grid == recursion
+    assert (peak_err(y, y64) < TOL).all()
+    assert (peak_err(dx, dx64) < TOL).all()
+    assert (param_grad_err(dp, dp64) < 10 * TOL).all()
+
+
+def test_compressor_lookahead_grads(cuda_device):
+    import dasp_pytorch_b200 as D
+    x, p01 = _inputs(4, 2, 30000, seed=7)
+    _check(cuda_device, D.compressor, oracle.compressor, x, denorm(p01, COMP_RANGES), extra={"lookahead_samples": 33})
+
+
+def test_expander_vs_oracle(cuda_device):
+    import dasp_pytorch_b200 as D
+    x, p01 = _inputs(6, 2, 40000, seed=8)
+    params = denorm(p01, COMP_RANGES)
+    params[1] = params[1].clamp(max=4.0)     # expansion ratio 1..4 keeps the gain in float range
+    _check(cuda_device, D.expander, oracle.expander, x, params)
+
+
+def test_compressor_identity_below_threshold_full_size(cuda_device):
+    """BASELINE config-3 size (512 x 2 x 48000): below T - W/2 the compressor is a pure makeup gain
+    (functional.py:352), whatever the smoother does; and the op is 1-homogeneous in nothing else."""
+    import dasp_pytorch_b200 as D
+    torch.manual_seed(0)
+    bs = 512
+    x = (torch.rand(bs, 2, 48000, device=cuda_device) * 2 - 1) * 1e-3     # peak -54 dBFS (sum of 2 ch)
+    one = torch.ones(bs, device=cuda_device)
+    mk = torch.linspace(0, 12, bs, device=cuda_device)
+    y = D.compressor(x, SR, -20 * one, 4 * one, 10 * one, 10 * one, 6 * one, mk)
+    expect = x * (10 ** (mk / 20)).view(bs, 1, 1)
+    assert torch.allclose(y, expect, rtol=3e-6, atol=0)
+    # ratio 1 is the identity for any level
+    x1 = torch.rand(bs, 2, 48000, device=cuda_device) * 2 - 1
+    y1 = D.compressor(x1, SR, -30 * one, one, 10 * one, 10 * one, 6 * one, 0 * one)
+    assert torch.allclose(y1, x1, rtol=3e-6, atol=0)
+
+
+def test_dynamics_param_contract(cuda_device):
+    import dasp_pytorch_b200 as D
+    x = torch.rand(3, 2, 2000, device=cuda_device) - 0.5
+    p = [torch.full((3,), v, device=cuda_device) for v in (-20.0, 4.0, 10.0, 50.0, 6.0, 3.0)]
+    y0 = D.compressor(x, SR, *p)
+    y1 = D.compressor(x, SR, *[q.view(3, 1) for q in p])            # any shape with bs elements
+    y2 = D.compressor(x, SR, threshold_db=p[0], ratio=p[1], attack_ms=p[2], release_ms=p[3] * 0 + 5, knee_db=p[4],
+                      makeup_gain_db=p[5])                          # keyword names are ABI; release ignored
+    assert torch.equal(y0, y1) and torch.equal(y0, y2)
+    with pytest.raises(RuntimeError):
+        D.compressor(x, SR, p[0][:2], *p[1:])
