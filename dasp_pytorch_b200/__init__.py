@@ -4,5 +4,6 @@ from dasp_pytorch_b200.functional import (  # noqa: F401
     distortion,
     compressor,
     expander,
+    parametric_eq,
 )
 from dasp_pytorch_b200 import functional  # noqa: F401

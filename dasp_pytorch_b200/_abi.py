@@ -37,6 +37,10 @@ _SIGNATURES = {
     "dasp_distortion_fwd": (c_int, [P, P, P, I64, I64, P]),
     "dasp_distortion_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, P]),
     "dasp_pointwise_bwd_workspace_floats": (I64, [I64, I64]),
+    "dasp_eq_tile_len": (I64, [I64]),
+    "dasp_eq_bwd_workspace_floats": (I64, [I64, I64]),
+    "dasp_eq_fwd": (c_int, [P, P, P, P, I64, I64, I64, c_float, P]),
+    "dasp_eq_bwd": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
     "dasp_dynamics_tile_len": (I64, [I64, I64]),
     "dasp_dynamics_fwd": (c_int, [c_int, P, P, P, P, P, P, P, P, I64, I64, I64, c_float, c_float, I64, P]),
     "dasp_dynamics_bwd": (c_int, [c_int, P, P, P, P, P, P, P, P, P, P, P, I64, I64, I64, c_float, c_float, I64, P]),

@@ -515,8 +515,10 @@ int dispatch(bool bwd, int w, const DynParams& p, int64_t bs, cudaStream_t st) {
 }
 
 int check_common(const float* x, const float* params5[5], int64_t bs, int64_t chs, int64_t n, int64_t lookahead) {
-  DASP_REQUIRE(x != nullptr, "dynamics: null x");
-  for (int i = 0; i < 5; ++i) DASP_REQUIRE(params5[i] != nullptr, "dynamics: null parameter pointer %d", i);
+  if (bs > 0 && n > 0) {
+    DASP_REQUIRE(x != nullptr, "dynamics: null x");
+    for (int i = 0; i < 5; ++i) DASP_REQUIRE(params5[i] != nullptr, "dynamics: null parameter pointer %d", i);
+  }
   DASP_REQUIRE(bs >= 0 && n >= 0 && chs >= 1, "dynamics: bad shape bs=%lld chs=%lld n=%lld", (long long)bs,
                (long long)chs, (long long)n);
   DASP_REQUIRE(chs <= kMaxChs, "dynamics: at most %d channels are supported, got %lld", kMaxChs, (long long)chs);
@@ -546,9 +548,9 @@ int dasp_dynamics_fwd(int kind, const float* x, const float* threshold_db, const
   const float* ps[5] = {threshold_db, ratio, attack_ms, knee_db, makeup_db};
   int rc = check_common(x, ps, bs, chs, n, lookahead);
   if (rc != DASP_OK) return rc;
-  DASP_REQUIRE(y != nullptr, "dynamics fwd: null y");
   DASP_REQUIRE(kind == 0 || kind == 1, "dynamics: kind must be 0 (compressor) or 1 (expander)");
   if (bs == 0 || n == 0) return DASP_OK;
+  DASP_REQUIRE(y != nullptr, "dynamics fwd: null y");
   const int w = pick_warps(bs, (int)chs, 2);
   const int tile_len = w * 32 * kE;
   DynParams p{};
@@ -568,12 +570,13 @@ int dasp_dynamics_bwd(int kind, const float* gy, const float* x, const float* th
   const float* ps[5] = {threshold_db, ratio, attack_ms, knee_db, makeup_db};
   int rc = check_common(x, ps, bs, chs, n, lookahead);
   if (rc != DASP_OK) return rc;
-  DASP_REQUIRE(gy && gx && gparams && ckpt, "dynamics bwd: null pointer");
   DASP_REQUIRE(kind == 0 || kind == 1, "dynamics: kind must be 0 (compressor) or 1 (expander)");
-  DASP_REQUIRE(lookahead == 0 || g_scratch != nullptr, "dynamics bwd: lookahead > 0 needs g_scratch (bs*n floats)");
   if (bs == 0) return DASP_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  DASP_REQUIRE(gparams != nullptr, "dynamics bwd: null gparams");
   if (n == 0) { DASP_CUDA_OK(cudaMemsetAsync(gparams, 0, sizeof(float) * 6 * bs, st)); return DASP_OK; }
+  DASP_REQUIRE(gy && gx && ckpt, "dynamics bwd: null pointer");
+  DASP_REQUIRE(lookahead == 0 || g_scratch != nullptr, "dynamics bwd: lookahead > 0 needs g_scratch (bs*n floats)");
   const int w = pick_warps(bs, (int)chs, 2);
   const int tile_len = w * 32 * kE;
   DynParams p{};

@@ -144,9 +144,9 @@ __global__ void reduce_param_grad_kernel(const float* __restrict__ partials, con
 
 template <Op OP>
 int launch_fwd(const float* x, const float* p_db, float* y, int64_t rows, int64_t n, cudaStream_t st) {
-  DASP_REQUIRE(x && p_db && y, "pointwise fwd: null pointer");
   DASP_REQUIRE(rows >= 0 && n >= 0, "pointwise fwd: negative size");
-  if (rows == 0 || n == 0) return DASP_OK;
+  if (rows == 0 || n == 0) return DASP_OK;          // empty tensors have null data pointers
+  DASP_REQUIRE(x && p_db && y, "pointwise fwd: null pointer");
   const int64_t tiles64 = (n + kTile - 1) / kTile;
   DASP_REQUIRE(rows * tiles64 < (1ll << 31), "pointwise fwd: rows*tiles = %lld exceeds the grid limit",
                (long long)(rows * tiles64));
@@ -162,10 +162,11 @@ int launch_fwd(const float* x, const float* p_db, float* y, int64_t rows, int64_
 template <Op OP>
 int launch_bwd(const float* gy, const float* x, const float* p_db, float* gx, float* g_param, float* ws,
                int64_t ws_floats, int64_t rows, int64_t n, cudaStream_t st) {
-  DASP_REQUIRE(gy && x && p_db && gx && g_param, "pointwise bwd: null pointer");
   DASP_REQUIRE(rows >= 0 && n >= 0, "pointwise bwd: negative size");
   if (rows == 0) return DASP_OK;
+  DASP_REQUIRE(g_param != nullptr, "pointwise bwd: null g_param");
   if (n == 0) { DASP_CUDA_OK(cudaMemsetAsync(g_param, 0, sizeof(float) * rows, st)); return DASP_OK; }
+  DASP_REQUIRE(gy && x && p_db && gx, "pointwise bwd: null pointer");
   const int64_t tiles64 = (n + kTile - 1) / kTile;
   DASP_REQUIRE(rows * tiles64 < (1ll << 31), "pointwise bwd: rows*tiles = %lld exceeds the grid limit",
                (long long)(rows * tiles64));

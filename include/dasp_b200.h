@@ -77,6 +77,21 @@ int dasp_dynamics_bwd(int kind, const float* gy, const float* x, const float* th
                       float* g_scratch, int64_t bs, int64_t chs, int64_t n, float sample_rate, float eps,
                       int64_t lookahead, void* stream);
 
+/* ---- parametric_eq: six cascaded biquads   (reference functional.py:118-272 with
+ *      signal.biquad signal.py:242-306 and signal.sosfilt_via_fsm signal.py:136-166) ------
+ * params is [bs][18] = (gain_dB, cutoff_Hz, Q) for low shelf, band0..band3, high shelf, i.e. the
+ * 18 tensors of the reference signature stacked in order; the same filter is applied to every
+ * channel of an item (signal.py:157-158).  ckpt (fwd: optional out, bwd: in) holds the twelve
+ * section states at every tile boundary: bs*chs * ceil(n / dasp_eq_tile_len(bs*chs)) * 12 floats.
+ * gparams is [bs][18]; ws needs dasp_eq_bwd_workspace_floats(bs, chs) floats. */
+int64_t dasp_eq_tile_len(int64_t rows);
+int64_t dasp_eq_bwd_workspace_floats(int64_t bs, int64_t chs);
+int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int64_t bs, int64_t chs,
+                int64_t n, float sample_rate, void* stream);
+int dasp_eq_bwd(const float* gy, const float* x, const float* params, const float* ckpt, float* gx,
+                float* gparams, float* ws, int64_t ws_floats, int64_t bs, int64_t chs, int64_t n,
+                float sample_rate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

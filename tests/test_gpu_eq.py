@@ -1,0 +1,124 @@
+"""parametric_eq on the GPU through the C ABI vs the CPU oracle and the reference golden.
+
+Tolerance (north star 1e-4 relative fp32) applied with the SURVEY.md 8c rule: per item
+err(new vs fp64 arbiter) <= max(1e-4, err(reference-arithmetic fp32 vs fp64 arbiter))."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+from helpers import SR, denorm, eq_ranges, param_grad_err, peak_err, run_with_grads
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _inputs(bs, chs, n, seed, low_corner=False):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.rand(bs, chs, n, generator=g) * 2 - 1
+    p01 = torch.rand(bs, 18, generator=g)
+    if low_corner:          # 20..140 Hz low shelf, 80..270 Hz band0: the ill-conditioned corner
+        p01[:, 1] = torch.rand(bs, generator=g) * 0.06
+        p01[:, 4] = torch.rand(bs, generator=g) * 0.1
+    return x, p01
+
+
+def _check(cuda_device, x, params, sr=SR, tail=0, strict=False):
+    import dasp_pytorch_b200 as D
+    y, dx, dp = run_with_grads(lambda xx, p: D.parametric_eq(xx, sr, *p), x, params, torch.float32, cuda_device)
+    y64, dx64, dp64 = run_with_grads(lambda xx, p: oracle.parametric_eq(xx, sr, *p, fsm_tail=tail), x, params,
+                                     torch.float64, "cpu")
+    y32, dx32, dp32 = run_with_grads(lambda xx, p: oracle.parametric_eq(xx, sr, *p, fsm_tail=tail), x, params,
+                                     torch.float32, "cpu")
+    for name, a, a32, a64 in (("y", y, y32, y64), ("dx", dx, dx32, dx64)):
+        e, e32 = peak_err(a, a64), peak_err(a32, a64)
+        lim = torch.full_like(e32, TOL) if strict else torch.clamp(e32, min=TOL)
+        assert (e <= lim).all(), (name, e, e32)
+    e, e32 = param_grad_err(dp, dp64), param_grad_err(dp32, dp64)
+    lim = torch.full_like(e32, TOL) if strict else torch.clamp(e32, min=TOL)
+    assert (e <= lim).all(), ("dparam", e, e32)
+    return peak_err(y, y64)
+
+
+def test_eq_golden(cuda_device):
+    import dasp_pytorch_b200 as D
+    g = load_golden("parametric_eq.npz")
+    names = [str(s) for s in g["names"]]
+    params = denorm(g["p01"], eq_ranges())
+    y, dx, dp = run_with_grads(lambda xx, p: D.parametric_eq(xx, SR, *p), g["x"], params, torch.float32, cuda_device)
+    # item 0 (20 Hz low shelf at N=4096) is where the reference itself time-aliases; see test_oracle_golden
+    assert peak_err(y, g["eq_y64"])[1:].max() < TOL
+    assert peak_err(dx, g["eq_dx64"])[1:].max() < TOL
+    ref = [torch.as_tensor(g[f"eq_d_{n}"]) for n in names]
+    assert param_grad_err(dp, ref)[1:].max() < TOL
+
+
+@pytest.mark.parametrize("bs,chs,n,low", [(16, 2, 48000, False), (16, 2, 48000, True), (5, 1, 48000, False)])
+def test_eq_full_ranges_vs_oracle(cuda_device, bs, chs, n, low):
+    """Processor parameter ranges (modules.py:136-155) at the BASELINE length; the sigma-form kernel is
+    held to the STRICT 1e-4 here even where the reference's own fp32 path is 10-100x worse."""
+    x, p01 = _inputs(bs, chs, n, seed=3, low_corner=low)
+    e = _check(cuda_device, x, denorm(p01, eq_ranges()), strict=True)
+    assert e.max() < 5e-5
+
+
+@pytest.mark.parametrize("bs,chs,n", [(2, 2, 4097), (3, 2, 100), (2, 1, 1), (2, 2, 480 * 4 + 4), (900, 2, 600),
+                                      (300, 2, 1000), (40, 3, 5000)])
+def test_eq_ragged_shapes(cuda_device, bs, chs, n):
+    """unaligned N (scalar path), N shorter than a tile, all warps-per-row variants, 3 channels.
+    Arbiter: alias-free oracle (enlarged FFT grid == true recursion)."""
+    x, p01 = _inputs(bs, chs, n, seed=4)
+    _check(cuda_device, x, denorm(p01, eq_ranges()), tail=1 << 18)
+
+
+def test_eq_other_sample_rates_and_param_forms(cuda_device):
+    import dasp_pytorch_b200 as D
+    x, p01 = _inputs(4, 2, 24000, seed=9)
+    for sr in (48000, 32000):
+        _check(cuda_device, x, denorm(p01, eq_ranges(sr)), sr=sr, tail=1 << 18)
+    # one-element parameters broadcast over the batch; integer cut-offs (examples/demo.py:44)
+    xs = x.to(cuda_device)
+    p = [torch.tensor([v], device=cuda_device) for v in (3.0, 200, 0.7, -2.0, 500, 1.0, 1.5, 3000, 2.0, -4.0, 9000,
+                                                         0.9, 2.0, 14000, 1.1, 6.0, 8000, 0.707)]
+    p[1] = torch.tensor([200], device=cuda_device, dtype=torch.int64)
+    y1 = D.parametric_eq(xs, SR, *p)
+    y2 = D.parametric_eq(xs, SR, *[q.float().expand(4).contiguous() for q in p])
+    assert torch.equal(y1, y2)
+    yo = oracle.parametric_eq(x.double(), SR, *[q.double().cpu() for q in p], fsm_tail=1 << 18)
+    assert peak_err(y1.cpu(), yo).max() < TOL
+    # gradient reaches a broadcast parameter (summed over the batch)
+    q0 = torch.tensor([3.0], device=cuda_device, requires_grad=True)
+    D.parametric_eq(xs, SR, q0, *p[1:]).pow(2).mean().backward()
+    q1 = torch.tensor([3.0], dtype=torch.float64, requires_grad=True)
+    oracle.parametric_eq(x.double(), SR, q1, *[q.double().cpu() for q in p[1:]], fsm_tail=1 << 18).pow(2).mean().backward()
+    assert abs(q0.grad.item() - q1.grad.item()) <= 1e-4 * abs(q1.grad.item())
+
+
+def test_eq_known_answers_full_size(cuda_device):
+    """BASELINE config-2 size (256 x 2 x 48000): 0 dB everywhere is the identity; linearity; impulse response
+    equals scipy's sosfilt of the designed sections."""
+    import dasp_pytorch_b200 as D
+    torch.manual_seed(0)
+    bs, chs, n = 256, 2, 48000
+    x = torch.rand(bs, chs, n, device=cuda_device) * 2 - 1
+    p01 = torch.rand(bs, 18)
+    params = [p.to(cuda_device) for p in denorm(p01, eq_ranges())]
+    flat = [p.clone() for p in params]
+    for k in range(6):
+        flat[3 * k] = torch.zeros(bs, device=cuda_device)
+    y = D.parametric_eq(x, SR, *flat)
+    assert (y - x).abs().max() < 2e-5                       # unity EQ at 0 dB gains
+    ya = D.parametric_eq(x, SR, *params)
+    yb = D.parametric_eq(0.5 * x, SR, *params)
+    assert torch.allclose(yb, 0.5 * ya, rtol=0, atol=1e-6 * float(ya.abs().max()))   # homogeneity (exact scaling by 2)
+    x2 = torch.rand(bs, chs, n, device=cuda_device) * 2 - 1
+    ysum = D.parametric_eq(x + x2, SR, *params)
+    y2 = D.parametric_eq(x2, SR, *params)
+    assert (ysum - (ya + y2)).abs().max() < 1e-4 * float(ysum.abs().max())           # additivity
+    # impulse response vs scipy on the first 8 items
+    imp = torch.zeros(8, 1, n, device=cuda_device)
+    imp[:, :, 0] = 1.0
+    h = D.parametric_eq(imp, SR, *[p[:8] for p in params]).cpu().double()
+    href = oracle.parametric_eq(imp.cpu().double(), SR, *[p[:8].cpu().double() for p in params], method="recursion")
+    assert peak_err(h, href).max() < 1e-5
