@@ -5,5 +5,6 @@ from dasp_pytorch_b200.functional import (  # noqa: F401
     compressor,
     expander,
     parametric_eq,
+    noise_shaped_reverberation,
 )
 from dasp_pytorch_b200 import functional  # noqa: F401

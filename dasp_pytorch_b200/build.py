@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write(logs[-1])
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [nvcc, "-shared", "-o", LIB, *objs, "-L", cuda_lib, "-lcufft", "-lcudart",
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-L", cuda_lib, "-lcufft", "-lcudart",
             "-Xlinker", f"-rpath={cuda_lib}"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     logs.append(f"$ {' '.join(link)}\n{r.stdout}")

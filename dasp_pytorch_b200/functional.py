@@ -78,6 +78,30 @@ def _ws(n_floats: int, device) -> torch.Tensor:
     return torch.empty(max(int(n_floats), 1), dtype=torch.float32, device=device)
 
 
+# bench.py sets this to a list to collect (stage, start_event, end_event) around every C-ABI call
+STAGE_TIMING = None
+
+
+class _timed:
+    """CUDA events on the launching stream around one C-ABI call (active only while benchmarking)."""
+
+    def __init__(self, name, device):
+        self.name, self.device = name, device
+
+    def __enter__(self):
+        if STAGE_TIMING is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if STAGE_TIMING is not None:
+            self.b.record(torch.cuda.current_stream(self.device))
+            STAGE_TIMING.append((self.name, self.a, self.b))
+        return False
+
+
 # --------------------------------------------------------------------------------------
 # gain / distortion
 # --------------------------------------------------------------------------------------
@@ -90,7 +114,7 @@ class _PointwiseFn(torch.autograd.Function):
     def forward(ctx, x, p_db, kind: str, rows: int, n: int):
         lib = _abi.lib()
         y = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _timed("dist_fwd", x.device):
             st = stream_ptr(x.device)
             if kind == "gain":
                 check(lib.dasp_gain_fwd(ptr(x), ptr(p_db), ptr(y), rows, 1, n, st), "dasp_gain_fwd")
@@ -110,7 +134,7 @@ class _PointwiseFn(torch.autograd.Function):
         gp = torch.empty_like(p_db)
         nws = lib.dasp_pointwise_bwd_workspace_floats(rows, n)
         ws = _ws(nws, x.device)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _timed("dist_bwd", x.device):
             st = stream_ptr(x.device)
             if ctx.kind == "gain":
                 check(lib.dasp_gain_bwd(ptr(gy), ptr(x), ptr(p_db), ptr(gx), ptr(gp), ptr(ws), nws, rows, 1, n, st),
@@ -170,9 +194,10 @@ class _DynamicsFn(torch.autograd.Function):
                 if tile <= 0:
                     raise DaspError(f"dynamics: unsupported channel count {chs}")
                 ckpt = torch.empty(bs * max(1, -(-n // tile)), dtype=torch.float32, device=x.device)
-            check(lib.dasp_dynamics_fwd(kind, ptr(x), ptr(threshold), ptr(ratio), ptr(attack), ptr(knee),
-                                        ptr(makeup), ptr(y), ptr(ckpt), bs, chs, n, float(sample_rate),
-                                        float(eps), int(lookahead), stream_ptr(x.device)), "dasp_dynamics_fwd")
+            with _timed("comp_fwd", x.device):
+                check(lib.dasp_dynamics_fwd(kind, ptr(x), ptr(threshold), ptr(ratio), ptr(attack), ptr(knee),
+                                            ptr(makeup), ptr(y), ptr(ckpt), bs, chs, n, float(sample_rate),
+                                            float(eps), int(lookahead), stream_ptr(x.device)), "dasp_dynamics_fwd")
         if need_bwd:
             ctx.save_for_backward(x, threshold, ratio, attack, knee, makeup, ckpt)
         ctx.cfg = (kind, float(sample_rate), float(eps), int(lookahead))
@@ -188,7 +213,7 @@ class _DynamicsFn(torch.autograd.Function):
         gx = torch.empty_like(x)
         gp = torch.empty(bs, 6, dtype=torch.float32, device=x.device)
         scratch = torch.empty(bs * n, dtype=torch.float32, device=x.device) if lookahead > 0 else None
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _timed("comp_bwd", x.device):
             check(lib.dasp_dynamics_bwd(kind, ptr(gy), ptr(x), ptr(threshold), ptr(ratio), ptr(attack), ptr(knee),
                                         ptr(makeup), ptr(ckpt), ptr(gx), ptr(gp), ptr(scratch), bs, chs, n,
                                         sample_rate, eps, lookahead, stream_ptr(x.device)), "dasp_dynamics_bwd")
@@ -283,8 +308,9 @@ class _ParametricEqFn(torch.autograd.Function):
             if need_bwd:
                 tile = lib.dasp_eq_tile_len(bs * chs)
                 ckpt = torch.empty(bs * chs * max(1, -(-n // tile)) * 12, dtype=torch.float32, device=x.device)
-            check(lib.dasp_eq_fwd(ptr(x), ptr(params), ptr(y), ptr(ckpt), bs, chs, n, float(sample_rate),
-                                  stream_ptr(x.device)), "dasp_eq_fwd")
+            with _timed("eq_fwd", x.device):
+                check(lib.dasp_eq_fwd(ptr(x), ptr(params), ptr(y), ptr(ckpt), bs, chs, n, float(sample_rate),
+                                      stream_ptr(x.device)), "dasp_eq_fwd")
         if need_bwd:
             ctx.save_for_backward(x, params, ckpt)
         ctx.sample_rate = float(sample_rate)
@@ -300,7 +326,7 @@ class _ParametricEqFn(torch.autograd.Function):
         gp = torch.empty_like(params)
         nws = lib.dasp_eq_bwd_workspace_floats(bs, chs)
         ws = _ws(nws, x.device)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _timed("eq_bwd", x.device):
             check(lib.dasp_eq_bwd(ptr(gy), ptr(x), ptr(params), ptr(ckpt), ptr(gx), ptr(gp), ptr(ws), nws, bs, chs, n,
                                   ctx.sample_rate, stream_ptr(x.device)), "dasp_eq_bwd")
         return gx, gp, None
@@ -355,4 +381,133 @@ def parametric_eq(
     return y.to(dt)
 
 
-# the remaining processors are appended below as their kernels land
+# --------------------------------------------------------------------------------------
+# noise-shaped reverberation
+# --------------------------------------------------------------------------------------
+
+import os as _os
+
+# items per pass of the reverb pipeline: small enough that the transient FFT buffers stay L2-resident
+# on B200, large enough to amortise launches (override for experiments with DASP_REVERB_CHUNK)
+REVERB_CHUNK_ITEMS = int(_os.environ.get("DASP_REVERB_CHUNK", "4"))
+
+
+class _ReverbFn(torch.autograd.Function):
+    """x (bs, 1|2, n), params (bs, 25) -> y (bs, 2, n)."""
+
+    @staticmethod
+    def forward(ctx, x, params, noise, seed, sample_rate, num_samples, taps, chunk):
+        lib = _abi.lib()
+        bs, in_chs, n = x.shape
+        dev = x.device
+        y = torch.empty(bs, 2, n, dtype=torch.float32, device=dev)
+        need_bwd = any(ctx.needs_input_grad[:2])
+        geom = _abi.ReverbGeom()
+        with torch.cuda.device(dev):
+            check(lib.dasp_reverb_geometry(bs, n, num_samples, taps, chunk, geom), "dasp_reverb_geometry")
+            ws = torch.empty(max(geom.fwd_workspace_bytes, 16), dtype=torch.uint8, device=dev)
+            wet = fsave = xspec = irspec = None
+            if need_bwd:
+                wet = torch.empty(geom.wet_floats, dtype=torch.float32, device=dev)
+                fsave = torch.empty(geom.f_floats, dtype=torch.float32, device=dev)
+                xspec = torch.empty(geom.spec_c64, dtype=torch.complex64, device=dev)
+                irspec = torch.empty(geom.spec_c64, dtype=torch.complex64, device=dev)
+            with _timed("reverb_fwd", dev):
+                check(lib.dasp_reverb_fwd(ptr(x), in_chs, ptr(params), ptr(noise), int(seed), ptr(y), ptr(wet),
+                                          ptr(fsave), ptr(xspec), ptr(irspec), ptr(ws), ws.numel(), bs, n, num_samples,
+                                          taps, chunk, float(sample_rate), stream_ptr(dev)), "dasp_reverb_fwd")
+        if need_bwd:
+            ctx.save_for_backward(x, params, wet, fsave, xspec, irspec)
+        ctx.cfg = (num_samples, taps, chunk, geom.bwd_workspace_bytes)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _abi.lib()
+        x, params, wet, fsave, xspec, irspec = ctx.saved_tensors
+        num_samples, taps, chunk, bwd_bytes = ctx.cfg
+        bs, in_chs, n = x.shape
+        dev = x.device
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        gp = torch.empty_like(params)
+        ws = torch.empty(max(bwd_bytes, 16), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev), _timed("reverb_bwd", dev):
+            check(lib.dasp_reverb_bwd(ptr(gy), ptr(x), in_chs, ptr(params), ptr(wet), ptr(fsave), ptr(xspec),
+                                      ptr(irspec), ptr(gx), ptr(gp), ptr(ws), ws.numel(), bs, n, num_samples, taps,
+                                      chunk, stream_ptr(dev)), "dasp_reverb_bwd")
+        return gx, gp, None, None, None, None, None, None
+
+
+def noise_shaped_reverberation(
+    x: torch.Tensor,
+    sample_rate: float,
+    band0_gain: torch.Tensor,
+    band1_gain: torch.Tensor,
+    band2_gain: torch.Tensor,
+    band3_gain: torch.Tensor,
+    band4_gain: torch.Tensor,
+    band5_gain: torch.Tensor,
+    band6_gain: torch.Tensor,
+    band7_gain: torch.Tensor,
+    band8_gain: torch.Tensor,
+    band9_gain: torch.Tensor,
+    band10_gain: torch.Tensor,
+    band11_gain: torch.Tensor,
+    band0_decay: torch.Tensor,
+    band1_decay: torch.Tensor,
+    band2_decay: torch.Tensor,
+    band3_decay: torch.Tensor,
+    band4_decay: torch.Tensor,
+    band5_decay: torch.Tensor,
+    band6_decay: torch.Tensor,
+    band7_decay: torch.Tensor,
+    band8_decay: torch.Tensor,
+    band9_decay: torch.Tensor,
+    band10_decay: torch.Tensor,
+    band11_decay: torch.Tensor,
+    mix: torch.Tensor,
+    num_samples: int = 65536,
+    num_bandpass_taps: int = 1023,
+    *,
+    noise: Optional[torch.Tensor] = None,
+):
+    """Filtered-noise artificial reverberation (reference ``functional.py:406-577``).
+
+    Twelve bands (12 Hz low-pass, ten octave band-passes, 18 kHz high-pass; ``signal.py:42-92``),
+    each a white-noise signal filtered by a ``num_bandpass_taps`` FIR, shaped by
+    ``exp(-(10*decay+1)*t)`` and its gain, averaged into a ``num_samples``-long stereo impulse
+    response that is convolved with the input; ``mix`` blends wet and dry.  Mono input is
+    duplicated and the output is always stereo, like the reference.
+
+    Keyword-only extension ``noise``: the reference draws
+    ``torch.randn(bs*2, 12, num_samples + num_bandpass_taps - 1)`` inside the call
+    (``functional.py:547-548``).  Pass that tensor here to reproduce a seeded reference call
+    exactly (parity tests); by default fresh N(0,1) noise is generated on the device with
+    Philox4x32-10, keyed by a seed taken from the default torch CPU generator (so
+    ``torch.manual_seed`` makes the call reproducible).
+    """
+    assert num_bandpass_taps % 2 == 1, "num_bandpass_taps must be odd"
+    xf, dt = _audio(x)
+    bs, chs, n = xf.shape
+    assert chs <= 2, "only mono/stereo signals are supported"
+    plist = (
+        band0_gain, band1_gain, band2_gain, band3_gain, band4_gain, band5_gain,
+        band6_gain, band7_gain, band8_gain, band9_gain, band10_gain, band11_gain,
+        band0_decay, band1_decay, band2_decay, band3_decay, band4_decay, band5_decay,
+        band6_decay, band7_decay, band8_decay, band9_decay, band10_decay, band11_decay,
+        mix,
+    )
+    packed = torch.stack([_param(p, bs, xf, f"noise_shaped_reverberation parameter {i}", allow_broadcast=True)
+                          for i, p in enumerate(plist)], dim=1).contiguous()
+    seed = 0
+    if noise is not None:
+        expect = (bs * 2, 12, num_samples + num_bandpass_taps - 1)
+        if tuple(noise.shape) != expect:
+            raise ValueError(f"noise must have shape {expect}, got {tuple(noise.shape)}")
+        noise = noise.to(device=xf.device, dtype=torch.float32).contiguous()
+    else:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    y = _ReverbFn.apply(xf, packed, noise, seed, sample_rate, int(num_samples), int(num_bandpass_taps),
+                        REVERB_CHUNK_ITEMS)
+    return y.to(dt)

@@ -92,6 +92,38 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
                 float* gparams, float* ws, int64_t ws_floats, int64_t bs, int64_t chs, int64_t n,
                 float sample_rate, void* stream);
 
+/* ---- noise_shaped_reverberation          (reference functional.py:406-577, filter bank
+ *      signal.octave_band_filterbank signal.py:42-92) --------------------------------------
+ * params is [bs][25] = 12 band gains, 12 band decays, mix (signature order).  x is (bs, in_chs, n)
+ * with in_chs 1 or 2; y is always (bs, 2, n) (mono is duplicated, functional.py:493-495).
+ * noise: NULL -> white noise is generated on the device (Philox4x32-10, keyed by `seed`);
+ *        else the (bs*2, 12, num_samples + taps - 1) tensor the reference would have drawn
+ *        (functional.py:547-548) -- the parity-test entry.
+ * Buffers kept for the backward (pass NULL for all four when no backward follows):
+ *   wet_save  bs*2*n floats, f_save  geom.f_floats floats (band-filtered noise blocks),
+ *   xspec_save / irspec_save  geom.spec_c64 complex64 each.
+ * workspace: geom.fwd_workspace_bytes / geom.bwd_workspace_bytes bytes of device memory. */
+typedef struct dasp_reverb_geom {
+  int64_t nb, hop, nbk, ls;   /* overlap-save block length, hop, blocks and slot length per band signal */
+  int64_t n2;                 /* FFT length of the audio convolution (>= n + num_samples - 1, 7-smooth) */
+  int64_t chunk_items;        /* items processed per pass (L2-sized working set) */
+  int64_t f_floats, spec_c64, wet_floats;
+  int64_t fwd_workspace_bytes, bwd_workspace_bytes;
+} dasp_reverb_geom;
+int dasp_reverb_geometry(int64_t bs, int64_t n, int64_t num_samples, int64_t taps, int64_t chunk_items,
+                         dasp_reverb_geom* out);
+int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const float* noise, uint64_t seed,
+                    float* y, float* wet_save, float* f_save, void* xspec_save, void* irspec_save,
+                    void* workspace, int64_t workspace_bytes, int64_t bs, int64_t n, int64_t num_samples,
+                    int64_t taps, int64_t chunk_items, float sample_rate, void* stream);
+int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float* params,
+                    const float* wet_save, const float* f_save, const void* xspec_save,
+                    const void* irspec_save, float* gx, float* gparams, void* workspace,
+                    int64_t workspace_bytes, int64_t bs, int64_t n, int64_t num_samples, int64_t taps,
+                    int64_t chunk_items, void* stream);
+/* host-only: the 12 x taps fp32 filter bank (scipy.signal.firwin restated; no GPU needed) */
+int dasp_reverb_filterbank(int64_t taps, double sample_rate, float* out);
+
 #ifdef __cplusplus
 }
 #endif

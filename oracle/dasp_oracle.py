@@ -383,12 +383,10 @@ def noise_shaped_reverberation(x, sample_rate, *params, num_samples: int = 65536
     ir = (shaped * env * gains).mean(dim=2)                              # functional.py:564-567
 
     if method == "direct":
-        xp = torch.nn.functional.pad(x, (num_samples - 1, 0))
-        wet = torch.stack([
-            torch.nn.functional.conv1d(xp[b : b + 1], torch.flip(ir[b], dims=[-1]).unsqueeze(1),
-                                       groups=2)[0]
-            for b in range(bs)
-        ])
+        # one grouped correlation over all (item, channel) rows == the reference's vmap(conv1d(groups=2))
+        xp = torch.nn.functional.pad(x, (num_samples - 1, 0)).reshape(1, bs * 2, n + num_samples - 1)
+        wet = torch.nn.functional.conv1d(xp, torch.flip(ir, dims=[-1]).reshape(bs * 2, 1, num_samples),
+                                         groups=bs * 2).reshape(bs, 2, n)
     else:
         m = 1 << math.ceil(math.log2(n + num_samples - 1))
         wet = torch.fft.irfft(torch.fft.rfft(x, m) * torch.fft.rfft(ir, m), m)[..., :n]
