@@ -314,8 +314,9 @@ def main():
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         e = samples_per_step
-        item_rev_fwd = (2 * N_SAMPLES * 4) * 2 + 2 * (2 * IR_LEN * 4)              # x in, y out, IR write + read
-        item_rev_bwd = 3 * (2 * N_SAMPLES * 4) + 2 * IR_LEN * 4 + 2 * (2 * IR_LEN * 4) + 2 * 12 * IR_LEN * 4
+        leff = min(IR_LEN, N_SAMPLES)       # only the first min(L, N) IR taps can reach the N outputs
+        item_rev_fwd = (2 * N_SAMPLES * 4) * 2 + 2 * (2 * leff * 4)                # x in, y out, IR write + read
+        item_rev_bwd = 3 * (2 * N_SAMPLES * 4) + 2 * leff * 4 + 2 * (2 * leff * 4) + 2 * 12 * leff * 4
         alg = {  # algorithmic bytes per launch: 8 B/sample fwd, 12 B/sample bwd for the streaming ops
             "eq_fwd": 8 * e, "eq_bwd": 12 * e, "comp_fwd": 8 * e, "comp_bwd": 12 * e, "dist_fwd": 8 * e,
             "dist_bwd": 12 * e, "reverb_fwd": item_rev_fwd * bs, "reverb_bwd": item_rev_bwd * bs,

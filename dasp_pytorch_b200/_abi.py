@@ -28,7 +28,7 @@ class ReverbGeom(ctypes.Structure):
     """mirror of ``dasp_reverb_geom`` (include/dasp_b200.h)"""
 
     _fields_ = [(name, c_int64) for name in (
-        "nb", "hop", "nbk", "ls", "n2", "chunk_items", "f_floats", "spec_c64", "wet_floats",
+        "nb", "hop", "nbk", "leff", "n2", "chunk_items", "f_floats", "spec_c64", "wet_floats",
         "fwd_workspace_bytes", "bwd_workspace_bytes")]
 
 P = c_void_p       # device pointer

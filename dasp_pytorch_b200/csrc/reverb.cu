@@ -8,15 +8,19 @@
 // convolutions.  Here both are FFT convolutions, batched through cuFFT,
 // with everything between the transforms fused into four streaming kernels:
 //
-//   IR synthesis (24 band signals per item):
-//     noise (user tensor in parity mode, Philox4x32-10 on device otherwise) laid out with one
-//     hop-aligned slot per band signal  ->  overlap-save: batched R2C of nb-point blocks read with
-//     an OVERLAPPING advanced layout (idist = hop < nb, no unfold copy)  ->  fused multiply by the
-//     cached band spectrum H_k/nb  ->  batched C2R (its output, the filtered noise f, is kept for the
-//     backward)  ->  fused envelope * gain * band-mean kernel writing the IR straight into the
-//     zero-padded input buffer of the next FFT.
-//   apply: R2C(x), R2C(IR) at n2 >= N+L-1 (7-smooth), fused complex multiply, C2R, fused crop +
-//     wet/dry mix.  The two spectra are kept for the backward.
+//   Only the first Leff = min(L, N) taps of the impulse response can reach the N output samples
+//   (y[n] = sum_{t<=n} IR[t] x[n-t], n < N), so only those are synthesised -- an exact saving (the
+//   reference computes the rest and then multiplies it by the zero padding).
+//   IR synthesis (12 bands x 2 channels per item):
+//     noise (user tensor in parity mode, Philox4x32-10 on device otherwise) written as overlap-save
+//     blocks of nb samples, the LEFT and RIGHT channel of a band packed as real/imag of one complex
+//     sequence (both channels see the same real filter, so one complex FFT filters both)  ->
+//     batched in-place C2C (single-kernel shared-memory cuFFT path)  ->  fused multiply by the cached
+//     band spectrum H_k/nb  ->  batched inverse C2C (its output, the filtered noise f, is kept for the
+//     backward)  ->  fused envelope * gain * band-mean kernel writing both channels of the IR straight
+//     into the zero-padded input buffer of the next FFT.
+//   apply: R2C(x), R2C(IR) at n2 >= N+Leff-1, fused complex multiply, C2R, fused crop + wet/dry mix.
+//     The two spectra are kept for the backward.
 //   Items are processed in chunks of a few items so the transient buffers (noise, block spectra)
 //   stay inside the 126 MB L2 instead of round-tripping through HBM between the passes.
 //
@@ -106,11 +110,22 @@ int64_t next_fast_even(int64_t v) {
   return v;
 }
 
+// FFT length for the audio convolution: 7-smooth and a multiple of a large power of two (measured on
+// B200: 98304 = 2^15*3 runs the C2R 2.3x faster than 96000 = 2^8*3*5^3)
+int64_t next_conv_len(int64_t v) {
+  int64_t step = 2;
+  while (step < 1024 && step * 64 <= v) step *= 2;
+  int64_t c = ((v + step - 1) / step) * step;
+  while (!is_7smooth(c)) c += step;
+  return c;
+}
+
 struct Geom {
   int64_t bs, n, L, taps, P;
-  int64_t nb, hop, nbk, ls, n2, chunk;
-  int64_t nbc() const { return nb / 2 + 1; }
+  int64_t leff;                 // min(L, n): the only IR taps that can reach the output
+  int64_t nb, hop, nbk, n2, chunk;
   int64_t n2c() const { return n2 / 2 + 1; }
+  int64_t pair_c64() const { return nbk * nb; }          // complex samples per (item, band) pair
 };
 
 int make_geom(int64_t bs, int64_t n, int64_t L, int64_t taps, int64_t chunk, Geom& g) {
@@ -123,9 +138,9 @@ int make_geom(int64_t bs, int64_t n, int64_t L, int64_t taps, int64_t chunk, Geo
   while (nb < 4 * (discard + 1)) nb *= 2;
   g.nb = nb;
   g.hop = nb - discard;
-  g.nbk = (L + g.P + g.hop - 1) / g.hop;
-  g.ls = g.nbk * g.hop;
-  g.n2 = next_fast_even(n + L - 1);
+  g.leff = L < n ? L : n;
+  g.nbk = (g.leff + g.hop - 1) / g.hop;
+  g.n2 = next_conv_len(n + g.leff - 1);
   if (chunk <= 0) chunk = 4;
   g.chunk = chunk < bs ? chunk : (bs > 0 ? bs : 1);
   return DASP_OK;
@@ -148,7 +163,7 @@ std::mutex g_mu;
 std::map<PlanKey, PlanVal> g_plans;
 std::map<FbKey, cufftComplex*> g_fb;
 
-int get_plan(int type /*0 = R2C, 1 = C2R*/, int64_t n, int64_t batch, int64_t idist, int64_t odist, PlanVal& out) {
+int get_plan(int type /*0 = R2C, 1 = C2R, 2 = C2C*/, int64_t n, int64_t batch, int64_t idist, int64_t odist, PlanVal& out) {
   int dev = 0;
   DASP_CUDA_OK(cudaGetDevice(&dev));
   PlanKey key{dev, type, n, batch, idist, odist};
@@ -158,63 +173,69 @@ int get_plan(int type /*0 = R2C, 1 = C2R*/, int64_t n, int64_t batch, int64_t id
   DASP_CUFFT_OK(cufftCreate(&pv.h));
   DASP_CUFFT_OK(cufftSetAutoAllocation(pv.h, 0));
   long long nn[1] = {(long long)n};
-  long long inembed[1] = {(long long)(type == 0 ? n : n / 2 + 1)};
+  long long inembed[1] = {(long long)(type == 1 ? n / 2 + 1 : n)};
   long long onembed[1] = {(long long)(type == 0 ? n / 2 + 1 : n)};
-  DASP_CUFFT_OK(cufftMakePlanMany64(pv.h, 1, nn, inembed, 1, (long long)idist, onembed, 1, (long long)odist,
-                                    type == 0 ? CUFFT_R2C : CUFFT_C2R, (long long)batch, &pv.work));
+  const cufftType ct = type == 0 ? CUFFT_R2C : (type == 1 ? CUFFT_C2R : CUFFT_C2C);
+  DASP_CUFFT_OK(cufftMakePlanMany64(pv.h, 1, nn, inembed, 1, (long long)idist, onembed, 1, (long long)odist, ct,
+                                    (long long)batch, &pv.work));
   g_plans[key] = pv;
   out = pv;
   return DASP_OK;
 }
 
 // ------------------------------------------------------------------ kernels
-// parity mode: user noise (rows*12 signals of L+P samples, contiguous) -> hop-aligned slots of ls samples
-__global__ void noise_layout_kernel(const float* __restrict__ noise, float* __restrict__ ws, int64_t sig0,
-                                    int64_t nsig, int64_t lp, int64_t ls, int64_t tail) {
-  const int64_t total = nsig * ls + tail;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    if (i < nsig * ls) {
-      const int64_t s = i / ls, t = i - s * ls;
-      if (t < lp) v = noise[(sig0 + s) * lp + t];
-    }
-    ws[i] = v;
+// Overlap-save block layout shared by the kernels below.  For item i (chunk-local), band k, block b,
+// sample m < nb the complex element  C[((i*12 + k)*nbk + b)*nb + m]  holds (left, right) of the band
+// signal at absolute noise position b*hop + m; after the two FFTs it holds the filtered noise f at time
+// t = b*hop + m - P (valid for P <= m < P + hop).
+
+// parity mode: gather the user noise (bs*2 rows x 12 bands x (L+P) samples) into the block layout
+__global__ void noise_pairs_layout_kernel(const float* __restrict__ noise, float2* __restrict__ C, int64_t item0,
+                                          int nbk, int nb, int hop, int64_t lp) {
+  // grid = (nbk, 12, items); threads stride over m
+  const int b = blockIdx.x, k = blockIdx.y;
+  const int64_t il = blockIdx.z;
+  const float* nl = noise + (((item0 + il) * 2 + 0) * kBands + k) * lp;
+  const float* nr = noise + (((item0 + il) * 2 + 1) * kBands + k) * lp;
+  float2* out = C + ((il * kBands + k) * nbk + b) * (int64_t)nb;
+  for (int m = threadIdx.x; m < nb; m += blockDim.x) {
+    const int64_t pos = (int64_t)b * hop + m;
+    float2 v = make_float2(0.f, 0.f);
+    if (pos < lp) v = make_float2(nl[pos], nr[pos]);
+    out[m] = v;
   }
 }
 
-// performance mode: N(0,1) from Philox4x32-10 (cuRAND device API), addressed by absolute position so the
-// stream does not depend on the chunking
-__global__ void noise_philox_kernel(float* __restrict__ ws, int64_t sig0, int64_t nsig, int64_t lp, int64_t ls,
-                                    int64_t tail, unsigned long long seed) {
-  const int64_t quads = (nsig * ls + tail) / 4;     // ls and tail are multiples of 4
-  for (int64_t qd = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; qd < quads; qd += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = qd * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (i < nsig * ls) {
-      const int64_t s = i / ls, t = i - s * ls;
-      if (t < lp) {
-        curandStatePhilox4_32_10_t st;
-        curand_init(seed, (unsigned long long)((sig0 + s) * (ls / 4) + t / 4), 0ull, &st);
-        v = curand_normal4(&st);
-        if (t + 1 >= lp) v.y = 0.f;
-        if (t + 2 >= lp) v.z = 0.f;
-        if (t + 3 >= lp) v.w = 0.f;
-      }
-    }
-    reinterpret_cast<float4*>(ws)[qd] = v;
+// performance mode: N(0,1) from Philox4x32-10 (cuRAND device API).  The stream of a band signal is
+// addressed by its absolute sample position, so the overlapping part of consecutive blocks is simply
+// generated twice and nothing depends on the chunking.
+__global__ void noise_pairs_philox_kernel(float2* __restrict__ C, int64_t item0, int nbk, int nb, int hop,
+                                          unsigned long long seed) {
+  const int b = blockIdx.x, k = blockIdx.y;
+  const int64_t il = blockIdx.z;
+  const unsigned long long sig_l = (unsigned long long)(((item0 + il) * 2 + 0) * kBands + k);
+  const unsigned long long sig_r = (unsigned long long)(((item0 + il) * 2 + 1) * kBands + k);
+  float4* out = reinterpret_cast<float4*>(C + ((il * kBands + k) * nbk + b) * (int64_t)nb);
+  for (int q4 = threadIdx.x; q4 < nb / 4; q4 += blockDim.x) {
+    const unsigned long long quad = (unsigned long long)(((int64_t)b * hop) / 4 + q4);   // hop % 4 == 0
+    curandStatePhilox4_32_10_t sl, sr;
+    curand_init(seed, (sig_l << 24) + quad, 0ull, &sl);
+    curand_init(seed, (sig_r << 24) + quad, 0ull, &sr);
+    const float4 l = curand_normal4(&sl), r = curand_normal4(&sr);
+    out[q4 * 2 + 0] = make_float4(l.x, r.x, l.y, r.y);
+    out[q4 * 2 + 1] = make_float4(l.z, r.z, l.w, r.w);
   }
 }
 
-// block spectra *= H_band  (H already carries the 1/nb of the unnormalised inverse transform)
-__global__ void cmul_filter_kernel(cufftComplex* __restrict__ spec, const cufftComplex* __restrict__ H, int64_t nblocks,
-                                   int64_t nbk, int64_t nbc) {
-  const int64_t total = nblocks * nbc;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t j = i / nbc, f = i - j * nbc;
-    const int band = (int)((j / nbk) % kBands);
-    const cufftComplex h = H[band * nbc + f];
-    const cufftComplex a = spec[i];
-    spec[i] = make_cuFloatComplex(a.x * h.x - a.y * h.y, a.x * h.y + a.y * h.x);
+// block spectra *= H_band (full nb-point spectrum of the real filter, 1/nb of the inverse FFT folded in)
+__global__ void cmul_filter_pairs_kernel(float2* __restrict__ C, const float2* __restrict__ H, int nbk, int nb) {
+  const int b = blockIdx.x, k = blockIdx.y;
+  const int64_t il = blockIdx.z;
+  float2* c = C + ((il * kBands + k) * nbk + b) * (int64_t)nb;
+  const float2* h = H + (int64_t)k * nb;
+  for (int f = threadIdx.x; f < nb; f += blockDim.x) {
+    const float2 a = c[f], w = h[f];
+    c[f] = make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x);
   }
 }
 
@@ -223,30 +244,39 @@ __device__ __forceinline__ float time_axis(int64_t t, int64_t L, float step) {
   return (t < L / 2) ? step * (float)t : 1.0f - step * (float)(L - 1 - t);
 }
 
-// IR[r][t] = (1/12) sum_k gain_k exp(-(10 decay_k + 1) tt) f[r,k,t]  for t < L, zero padding up to n2
-// f lives in overlap-save blocks: sample t of signal s is block s*nbk + t/hop, offset t%hop + P.
-__global__ void shape_ir_kernel(const float* __restrict__ f, const float* __restrict__ params /* chunk x 25 */,
-                                float* __restrict__ irpad, int64_t rows, int64_t L, int64_t n2, int64_t nb,
-                                int64_t hop, int64_t nbk, int64_t P) {
-  const int64_t total = rows * n2;
+// IR[c][t] = (1/12) sum_k gain_k exp(-(10 decay_k + 1) tt(t)) f_c[k][t]  for t < leff, zero up to n2.
+// grid = (ceil(n2 / hop), items): CTA (b, item) writes samples [b*hop, (b+1)*hop) of both channel rows.
+__global__ void shape_ir_pairs_kernel(const float2* __restrict__ C, const float* __restrict__ params /* chunk x 25 */,
+                                      float* __restrict__ irpad, int64_t L, int64_t leff, int64_t n2, int nbk, int nb,
+                                      int hop, int P) {
+  const int b = blockIdx.x;
+  const int64_t il = blockIdx.y;
+  __shared__ float gk[kBands], rk[kBands];
+  if (threadIdx.x < kBands) {
+    gk[threadIdx.x] = params[il * 25 + threadIdx.x] * (1.0f / kBands);
+    rk[threadIdx.x] = -(params[il * 25 + kBands + threadIdx.x] * 10.0f + 1.0f);
+  }
+  __syncthreads();
   const float step = 1.0f / (float)(L - 1);
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / n2, t = i - r * n2;
-    float out = 0.f;
-    if (t < L) {
-      const float* pp = params + (r >> 1) * 25;
+  float* outl = irpad + (il * 2 + 0) * n2;
+  float* outr = irpad + (il * 2 + 1) * n2;
+  for (int m = threadIdx.x; m < hop; m += blockDim.x) {
+    const int64_t t = (int64_t)b * hop + m;
+    if (t >= n2) break;
+    float al = 0.f, ar = 0.f;
+    if (t < leff) {
       const float tt = time_axis(t, L, step);
-      const int64_t blk = t / hop, o = t - blk * hop + P;
-      float acc = 0.f;
+      const float2* c = C + ((il * kBands) * nbk + b) * (int64_t)nb + m + P;
 #pragma unroll
       for (int k = 0; k < kBands; ++k) {
-        const float fv = f[((r * kBands + k) * nbk + blk) * nb + o];
-        const float env = expf(-(pp[kBands + k] * 10.0f + 1.0f) * tt);
-        acc = fmaf(pp[k] * env, fv, acc);
+        const float2 v = c[(int64_t)k * nbk * nb];
+        const float e = gk[k] * expf(rk[k] * tt);
+        al = fmaf(e, v.x, al);
+        ar = fmaf(e, v.y, ar);
       }
-      out = acc * (1.0f / kBands);
     }
-    irpad[i] = out;
+    outl[t] = al;
+    outr[t] = ar;
   }
 }
 
@@ -351,47 +381,55 @@ __global__ void finish_dx_kernel(const float* __restrict__ gy, const float* __re
   }
 }
 
-// partial sums over a time slab for one (item, band): S0 = sum dIR env f ; S1 = sum dIR env f tt   (both channels)
-__global__ void ir_grad_kernel(const float* __restrict__ dir_pad, const float* __restrict__ f,
-                               const float* __restrict__ params, float* __restrict__ part, int64_t L, int64_t n2,
-                               int64_t nb, int64_t hop, int64_t nbk, int64_t P, int slabs) {
-  // grid = (slabs, 12, items_in_chunk); part[((item*12 + k)*slabs + slab)*2 + {0,1}]
-  const int slab = blockIdx.x, k = blockIdx.y;
-  const int64_t bl = blockIdx.z;
-  const float decay = params[bl * 25 + kBands + k];
-  const float rate = -(decay * 10.0f + 1.0f);
+// per (item, block): S0[k] = sum_t (dIR_l f_l + dIR_r f_r) env_k ;  S1[k] = sum_t (...) env_k tt
+// part[((item*nbk + b)*12 + k)*2 + {0,1}]
+__global__ void ir_grad_pairs_kernel(const float* __restrict__ dir_pad, const float2* __restrict__ C,
+                                     const float* __restrict__ params, float* __restrict__ part, int64_t L,
+                                     int64_t leff, int64_t n2, int nbk, int nb, int hop, int P) {
+  const int b = blockIdx.x;
+  const int64_t il = blockIdx.y;
+  __shared__ float rk[kBands];
+  __shared__ float red[8][2 * kBands];
+  if (threadIdx.x < kBands) rk[threadIdx.x] = -(params[il * 25 + kBands + threadIdx.x] * 10.0f + 1.0f);
+  __syncthreads();
   const float step = 1.0f / (float)(L - 1);
-  const int64_t per = (L + slabs - 1) / slabs;
-  const int64_t t0 = (int64_t)slab * per, t1 = (t0 + per < L) ? t0 + per : L;
-  float s0 = 0.f, s1 = 0.f;
-  for (int c = 0; c < 2; ++c) {
-    const int64_t r = bl * 2 + c;
-    const float* fr = f + (r * kBands + k) * nbk * nb;
-    const float* dr = dir_pad + r * n2;
-    for (int64_t t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
-      const float tt = time_axis(t, L, step);
-      const int64_t blk = t / hop;
-      const float v = dr[t] * expf(rate * tt) * fr[blk * nb + (t - blk * hop) + P];
-      s0 += v;
-      s1 = fmaf(v, tt, s1);
+  const float* dl = dir_pad + (il * 2 + 0) * n2;
+  const float* dr = dir_pad + (il * 2 + 1) * n2;
+  float s0[kBands], s1[kBands];
+#pragma unroll
+  for (int k = 0; k < kBands; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
+  for (int m = threadIdx.x; m < hop; m += blockDim.x) {
+    const int64_t t = (int64_t)b * hop + m;
+    if (t >= leff) break;
+    const float tt = time_axis(t, L, step);
+    const float gl = dl[t], gr = dr[t];
+    const float2* c = C + ((il * kBands) * nbk + b) * (int64_t)nb + m + P;
+#pragma unroll
+    for (int k = 0; k < kBands; ++k) {
+      const float2 v = c[(int64_t)k * nbk * nb];
+      const float w = fmaf(gl, v.x, gr * v.y) * expf(rk[k] * tt);
+      s0[k] += w;
+      s1[k] = fmaf(w, tt, s1[k]);
     }
   }
-  __shared__ float wp[2][32];
-  s0 = warp_sum(s0); s1 = warp_sum(s1);
-  if ((threadIdx.x & 31) == 0) { wp[0][threadIdx.x >> 5] = s0; wp[1][threadIdx.x >> 5] = s1; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kBands; ++k) {
+    const float a = warp_sum(s0[k]), c1 = warp_sum(s1[k]);
+    if (lane == 0) { red[warp][2 * k] = a; red[warp][2 * k + 1] = c1; }
+  }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    float a = 0.f, b = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += wp[0][w]; b += wp[1][w]; }
-    float* o = part + ((bl * kBands + k) * slabs + slab) * 2;
-    o[0] = a; o[1] = b;
+  if (threadIdx.x < 2 * kBands) {
+    float a = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) a += red[w][threadIdx.x];
+    part[((il * nbk + b) * kBands) * 2 + threadIdx.x] = a;
   }
 }
 
 // one thread per (item, param): gains (0..11), decays (12..23), mix (24)
 __global__ void reverb_param_grad_kernel(const float* __restrict__ ir_part, const float* __restrict__ mix_part,
                                          const float* __restrict__ params, float* __restrict__ gparams, int64_t item0,
-                                         int64_t items, int slabs, int mix_blocks) {
+                                         int64_t items, int nbk, int mix_blocks) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= items * 25) return;
   const int64_t bl = idx / 25;
@@ -400,8 +438,8 @@ __global__ void reverb_param_grad_kernel(const float* __restrict__ ir_part, cons
   double s = 0.0;
   if (q < 24) {
     const int k = q % kBands;
-    const float* pr = ir_part + ((bl * kBands + k) * slabs) * 2 + (q < kBands ? 0 : 1);
-    for (int i = 0; i < slabs; ++i) s += (double)pr[2 * i];
+    const float* pr = ir_part + (bl * nbk * kBands + k) * 2 + (q < kBands ? 0 : 1);
+    for (int i = 0; i < nbk; ++i) s += (double)pr[(int64_t)i * kBands * 2];
     if (q < kBands) s *= (1.0 / kBands);
     else s *= (double)pp[k] * (-10.0 / kBands);
   } else {
@@ -419,51 +457,47 @@ inline unsigned grid_for(int64_t total, int threads = 256) {
   return (unsigned)blocks;
 }
 
-// device-resident band spectra H_k (12 x nbc complex), scaled by 1/nb; built once per (device, taps, sr, nb)
-int get_filterbank(const Geom& g, double sr, cudaStream_t st, const cufftComplex** out) {
+// device-resident band spectra H_k: 12 x nb complex (full spectrum of the real taps), scaled by 1/nb;
+// built once per (device, taps, sr, nb)
+int get_filterbank(const Geom& g, double sr, cudaStream_t st, const float2** out) {
   int dev = 0;
   DASP_CUDA_OK(cudaGetDevice(&dev));
   FbKey key{dev, g.taps, g.nb, sr};
   auto it = g_fb.find(key);
-  if (it != g_fb.end()) { *out = it->second; return DASP_OK; }
+  if (it != g_fb.end()) { *out = reinterpret_cast<const float2*>(it->second); return DASP_OK; }
   DASP_REQUIRE(sr / 2.0 > 18000.0, "sample_rate %.1f too low: the filter bank needs 18 kHz < sr/2 (signal.py:84)", sr);
   std::vector<float> taps;
   octave_filterbank((int)g.taps, sr, taps);
-  std::vector<float> padded((size_t)kBands * g.nb, 0.f);
+  std::vector<float2> padded((size_t)kBands * g.nb, make_float2(0.f, 0.f));
   const float inv = 1.0f / (float)g.nb;
   for (int k = 0; k < kBands; ++k)
-    for (int64_t i = 0; i < g.taps; ++i) padded[(size_t)k * g.nb + i] = taps[(size_t)k * g.taps + i] * inv;
-  float* d_in = nullptr;
-  cufftComplex* d_out = nullptr;
+    for (int64_t i = 0; i < g.taps; ++i) padded[(size_t)k * g.nb + i].x = taps[(size_t)k * g.taps + i] * inv;
+  cufftComplex* d_buf = nullptr;
   void* d_work = nullptr;
-  DASP_CUDA_OK(cudaMalloc(&d_in, sizeof(float) * padded.size()));
-  DASP_CUDA_OK(cudaMalloc(&d_out, sizeof(cufftComplex) * kBands * g.nbc()));
-  DASP_CUDA_OK(cudaMemcpyAsync(d_in, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice, st));
+  DASP_CUDA_OK(cudaMalloc(&d_buf, sizeof(cufftComplex) * padded.size()));
+  DASP_CUDA_OK(cudaMemcpyAsync(d_buf, padded.data(), sizeof(float2) * padded.size(), cudaMemcpyHostToDevice, st));
   PlanVal pv;
-  int rc = get_plan(0, g.nb, kBands, g.nb, g.nbc(), pv);
+  int rc = get_plan(2, g.nb, kBands, g.nb, g.nb, pv);
   if (rc != DASP_OK) return rc;
   DASP_CUDA_OK(cudaMalloc(&d_work, pv.work > 0 ? pv.work : 16));
   DASP_CUFFT_OK(cufftSetStream(pv.h, st));
   DASP_CUFFT_OK(cufftSetWorkArea(pv.h, d_work));
-  DASP_CUFFT_OK(cufftExecR2C(pv.h, d_in, d_out));
+  DASP_CUFFT_OK(cufftExecC2C(pv.h, d_buf, d_buf, CUFFT_FORWARD));
   DASP_CUDA_OK(cudaStreamSynchronize(st));   // one-off (cache fill): host vector and temp buffers die here
-  cudaFree(d_in);
   cudaFree(d_work);
-  g_fb[key] = d_out;
-  *out = d_out;
+  g_fb[key] = d_buf;
+  *out = reinterpret_cast<const float2*>(d_buf);
   return DASP_OK;
 }
 
-struct Plans { PlanVal blk_r2c, blk_c2r, big_r2c, big_c2r; size_t work; };
+struct Plans { PlanVal blk_c2c, big_r2c, big_c2r; size_t work; };
 int get_plans(const Geom& g, int64_t items, Plans& p) {
   int rc;
-  const int64_t nblocks = items * kSig * g.nbk;
-  if ((rc = get_plan(0, g.nb, nblocks, g.hop, g.nbc(), p.blk_r2c)) != DASP_OK) return rc;
-  if ((rc = get_plan(1, g.nb, nblocks, g.nbc(), g.nb, p.blk_c2r)) != DASP_OK) return rc;
+  const int64_t nblocks = items * kBands * g.nbk;
+  if ((rc = get_plan(2, g.nb, nblocks, g.nb, g.nb, p.blk_c2c)) != DASP_OK) return rc;
   if ((rc = get_plan(0, g.n2, items * 2, g.n2, g.n2c(), p.big_r2c)) != DASP_OK) return rc;
   if ((rc = get_plan(1, g.n2, items * 2, g.n2c(), g.n2, p.big_c2r)) != DASP_OK) return rc;
-  p.work = p.blk_r2c.work;
-  if (p.blk_c2r.work > p.work) p.work = p.blk_c2r.work;
+  p.work = p.blk_c2c.work;
   if (p.big_r2c.work > p.work) p.work = p.big_r2c.work;
   if (p.big_c2r.work > p.work) p.work = p.big_c2r.work;
   return DASP_OK;
@@ -471,23 +505,20 @@ int get_plans(const Geom& g, int64_t items, Plans& p) {
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// workspace carve-up shared by geometry query and the two entry points
-struct FwdWs { size_t noise, bspec, irpad, xpad, yspec, xsp, isp, fchunk, cufft, total; };
+// workspace carve-up shared by the geometry query and the two entry points
+struct FwdWs { size_t irpad, xpad, yspec, xsp, isp, fchunk, cufft, total; };
 struct BwdWs { size_t gpad, bpad, gspec, aspec, bspec, irpart, mixpart, cufft, total; };
-constexpr int kIrSlabs = 16;
 constexpr int kMixBlocks = 32;
 
 void fwd_layout(const Geom& g, size_t cufft_work, FwdWs& w) {
   size_t o = 0;
-  w.noise = o; o += align256(sizeof(float) * (size_t)(g.chunk * kSig * g.ls + g.nb));
-  w.bspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * kSig * g.nbk * g.nbc()));
   w.irpad = o; o += align256(sizeof(float) * (size_t)(g.chunk * 2 * g.n2));
   w.xpad = o;  o += align256(sizeof(float) * (size_t)(g.chunk * 2 * g.n2));
   w.yspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
   // transient homes for what a forward WITHOUT a backward does not keep (null *_save pointers)
   w.xsp = o;   o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
   w.isp = o;   o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
-  w.fchunk = o; o += align256(sizeof(float) * (size_t)(g.chunk * kSig * g.nbk * g.nb));
+  w.fchunk = o; o += align256(sizeof(float2) * (size_t)(g.chunk * kBands * g.pair_c64()));
   w.cufft = o; o += align256(cufft_work);
   w.total = o;
 }
@@ -498,7 +529,7 @@ void bwd_layout(const Geom& g, size_t cufft_work, BwdWs& w) {
   w.gspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
   w.aspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
   w.bspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
-  w.irpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * kBands * kIrSlabs * 2));
+  w.irpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * g.nbk * kBands * 2));
   w.mixpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * 2 * kMixBlocks));
   w.cufft = o; o += align256(cufft_work);
   w.total = o;
@@ -530,6 +561,20 @@ int dasp_reverb_filterbank(int64_t taps, double sample_rate, float* out) {
   return DASP_OK;
 }
 
+namespace {
+int plans_for(const Geom& g, Plans& pfull, Plans& prem, size_t& work) {
+  int rc;
+  if ((rc = get_plans(g, g.chunk, pfull)) != DASP_OK) return rc;
+  work = pfull.work;
+  const int64_t rem = g.bs % g.chunk;
+  if (rem) {
+    if ((rc = get_plans(g, rem, prem)) != DASP_OK) return rc;
+    if (prem.work > work) work = prem.work;
+  }
+  return DASP_OK;
+}
+}  // namespace
+
 int dasp_reverb_geometry(int64_t bs, int64_t n, int64_t num_samples, int64_t taps, int64_t chunk_items,
                          dasp_reverb_geom* out) {
   DASP_REQUIRE(out != nullptr, "reverb geometry: null out");
@@ -537,23 +582,16 @@ int dasp_reverb_geometry(int64_t bs, int64_t n, int64_t num_samples, int64_t tap
   int rc = make_geom(bs, n, num_samples, taps, chunk_items, g);
   if (rc != DASP_OK) return rc;
   std::lock_guard<std::mutex> lk(g_mu);
-  Plans p{};
   size_t work = 0;
   if (bs > 0) {
-    if ((rc = get_plans(g, g.chunk, p)) != DASP_OK) return rc;
-    work = p.work;
-    const int64_t rem = bs % g.chunk;
-    if (rem) {
-      Plans q{};
-      if ((rc = get_plans(g, rem, q)) != DASP_OK) return rc;
-      if (q.work > work) work = q.work;
-    }
+    Plans p{}, q{};
+    if ((rc = plans_for(g, p, q, work)) != DASP_OK) return rc;
   }
   FwdWs fw; BwdWs bw;
   fwd_layout(g, work, fw);
   bwd_layout(g, work, bw);
-  out->nb = g.nb; out->hop = g.hop; out->nbk = g.nbk; out->ls = g.ls; out->n2 = g.n2; out->chunk_items = g.chunk;
-  out->f_floats = bs * kSig * g.nbk * g.nb;
+  out->nb = g.nb; out->hop = g.hop; out->nbk = g.nbk; out->leff = g.leff; out->n2 = g.n2; out->chunk_items = g.chunk;
+  out->f_floats = bs * kBands * g.pair_c64() * 2;
   out->spec_c64 = bs * 2 * g.n2c();
   out->wet_floats = bs * 2 * n;
   out->fwd_workspace_bytes = (int64_t)fw.total;
@@ -573,17 +611,11 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
   DASP_REQUIRE(x && params && y && workspace, "reverb fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lk(g_mu);
-  const cufftComplex* H = nullptr;
+  const float2* H = nullptr;
   if ((rc = get_filterbank(g, (double)sample_rate, st, &H)) != DASP_OK) return rc;
-  Plans pfull{};
-  if ((rc = get_plans(g, g.chunk, pfull)) != DASP_OK) return rc;
-  size_t work = pfull.work;
-  Plans prem{};
-  const int64_t rem = bs % g.chunk;
-  if (rem) {
-    if ((rc = get_plans(g, rem, prem)) != DASP_OK) return rc;
-    if (prem.work > work) work = prem.work;
-  }
+  Plans pfull{}, prem{};
+  size_t work = 0;
+  if ((rc = plans_for(g, pfull, prem, work)) != DASP_OK) return rc;
   FwdWs w;
   fwd_layout(g, work, w);
   if ((int64_t)w.total > workspace_bytes) {
@@ -591,41 +623,37 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     return DASP_ERR_WORKSPACE;
   }
   unsigned char* base = (unsigned char*)workspace;
-  float* ws_noise = (float*)(base + w.noise);
-  cufftComplex* ws_bspec = (cufftComplex*)(base + w.bspec);
   float* ws_irpad = (float*)(base + w.irpad);
   float* ws_xpad = (float*)(base + w.xpad);
   cufftComplex* ws_yspec = (cufftComplex*)(base + w.yspec);
   void* ws_cufft = base + w.cufft;
   const int64_t lp = g.L + g.P;
+  const int nbk = (int)g.nbk, nb = (int)g.nb, hop = (int)g.hop, P = (int)g.P;
 
   for (int64_t item0 = 0; item0 < bs; item0 += g.chunk) {
     const int64_t items = (bs - item0 < g.chunk) ? bs - item0 : g.chunk;
     const Plans& pl = (items == g.chunk) ? pfull : prem;
-    const int64_t nsig = items * kSig, rows = items * 2, nblocks = nsig * g.nbk;
+    const int64_t rows = items * 2;
     // kept for the backward when the caller passes *_save buffers, transient workspace otherwise
-    float* f_chunk = f_save ? f_save + item0 * kSig * g.nbk * g.nb : (float*)(base + w.fchunk);
+    float2* C = f_save ? reinterpret_cast<float2*>(f_save) + item0 * kBands * g.pair_c64()
+                       : reinterpret_cast<float2*>(base + w.fchunk);
     cufftComplex* xs = xspec_save ? (cufftComplex*)xspec_save + item0 * 2 * g.n2c() : (cufftComplex*)(base + w.xsp);
     cufftComplex* is = irspec_save ? (cufftComplex*)irspec_save + item0 * 2 * g.n2c() : (cufftComplex*)(base + w.isp);
+    const dim3 gblk((unsigned)nbk, kBands, (unsigned)items);
 
     // ---- IR synthesis ----
-    if (noise)
-      noise_layout_kernel<<<grid_for(nsig * g.ls + g.nb), 256, 0, st>>>(noise, ws_noise, item0 * kSig, nsig, lp, g.ls, g.nb);
-    else
-      noise_philox_kernel<<<grid_for((nsig * g.ls + g.nb) / 4), 256, 0, st>>>(ws_noise, item0 * kSig, nsig, lp, g.ls, g.nb,
-                                                                              (unsigned long long)seed);
+    if (noise) noise_pairs_layout_kernel<<<gblk, 256, 0, st>>>(noise, C, item0, nbk, nb, hop, lp);
+    else       noise_pairs_philox_kernel<<<gblk, 256, 0, st>>>(C, item0, nbk, nb, hop, (unsigned long long)seed);
     DASP_LAUNCH_OK("reverb noise kernel");
-    DASP_CUFFT_OK(cufftSetStream(pl.blk_r2c.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.blk_r2c.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecR2C(pl.blk_r2c.h, ws_noise, ws_bspec));
-    cmul_filter_kernel<<<grid_for(nblocks * g.nbc()), 256, 0, st>>>(ws_bspec, H, nblocks, g.nbk, g.nbc());
-    DASP_LAUNCH_OK("cmul_filter_kernel");
-    DASP_CUFFT_OK(cufftSetStream(pl.blk_c2r.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.blk_c2r.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecC2R(pl.blk_c2r.h, ws_bspec, f_chunk));
-    shape_ir_kernel<<<grid_for(rows * g.n2), 256, 0, st>>>(f_chunk, params + item0 * 25, ws_irpad, rows, g.L, g.n2, g.nb,
-                                                          g.hop, g.nbk, g.P);
-    DASP_LAUNCH_OK("shape_ir_kernel");
+    DASP_CUFFT_OK(cufftSetStream(pl.blk_c2c.h, st));
+    DASP_CUFFT_OK(cufftSetWorkArea(pl.blk_c2c.h, ws_cufft));
+    DASP_CUFFT_OK(cufftExecC2C(pl.blk_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_FORWARD));
+    cmul_filter_pairs_kernel<<<gblk, 256, 0, st>>>(C, H, nbk, nb);
+    DASP_LAUNCH_OK("cmul_filter_pairs_kernel");
+    DASP_CUFFT_OK(cufftExecC2C(pl.blk_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_INVERSE));
+    shape_ir_pairs_kernel<<<dim3((unsigned)((g.n2 + hop - 1) / hop), (unsigned)items), 256, 0, st>>>(
+        C, params + item0 * 25, ws_irpad, g.L, g.leff, g.n2, nbk, nb, hop, P);
+    DASP_LAUNCH_OK("shape_ir_pairs_kernel");
 
     // ---- apply ----
     pad_x_kernel<<<grid_for(rows * g.n2), 256, 0, st>>>(x, ws_xpad, item0, rows, n, g.n2, (int)in_chs);
@@ -658,15 +686,9 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
                "reverb bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lk(g_mu);
-  Plans pfull{};
-  if ((rc = get_plans(g, g.chunk, pfull)) != DASP_OK) return rc;
-  size_t work = pfull.work;
-  Plans prem{};
-  const int64_t rem = bs % g.chunk;
-  if (rem) {
-    if ((rc = get_plans(g, rem, prem)) != DASP_OK) return rc;
-    if (prem.work > work) work = prem.work;
-  }
+  Plans pfull{}, prem{};
+  size_t work = 0;
+  if ((rc = plans_for(g, pfull, prem, work)) != DASP_OK) return rc;
   BwdWs w;
   bwd_layout(g, work, w);
   if ((int64_t)w.total > workspace_bytes) {
@@ -683,12 +705,13 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
   float* ws_mixpart = (float*)(base + w.mixpart);
   void* ws_cufft = base + w.cufft;
   const float inv_n2 = 1.0f / (float)g.n2;
+  const int nbk = (int)g.nbk, nb = (int)g.nb, hop = (int)g.hop, P = (int)g.P;
 
   for (int64_t item0 = 0; item0 < bs; item0 += g.chunk) {
     const int64_t items = (bs - item0 < g.chunk) ? bs - item0 : g.chunk;
     const Plans& pl = (items == g.chunk) ? pfull : prem;
     const int64_t rows = items * 2;
-    const float* f_chunk = f_save + item0 * kSig * g.nbk * g.nb;
+    const float2* C = reinterpret_cast<const float2*>(f_save) + item0 * kBands * g.pair_c64();
     const cufftComplex* xs = (const cufftComplex*)xspec_save + item0 * 2 * g.n2c();
     const cufftComplex* is = (const cufftComplex*)irspec_save + item0 * 2 * g.n2c();
 
@@ -704,16 +727,15 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
     DASP_CUFFT_OK(cufftSetStream(pl.big_c2r.h, st));
     DASP_CUFFT_OK(cufftSetWorkArea(pl.big_c2r.h, ws_cufft));
     DASP_CUFFT_OK(cufftExecC2R(pl.big_c2r.h, ws_aspec, ws_gpad));       // gpad reused: dL/dx correlation term
-    DASP_CUFFT_OK(cufftExecC2R(pl.big_c2r.h, ws_bspec, ws_bpad));       // dL/dIR (first L samples)
+    DASP_CUFFT_OK(cufftExecC2R(pl.big_c2r.h, ws_bspec, ws_bpad));       // dL/dIR (first leff samples)
     finish_dx_kernel<<<grid_for(items * in_chs * n), 256, 0, st>>>(gy, ws_gpad, params, gx, item0, items, n, g.n2,
                                                                    (int)in_chs);
     DASP_LAUNCH_OK("finish_dx_kernel");
-    ir_grad_kernel<<<dim3(kIrSlabs, kBands, (unsigned)items), 256, 0, st>>>(ws_bpad, f_chunk, params + item0 * 25,
-                                                                            ws_irpart, g.L, g.n2, g.nb, g.hop, g.nbk, g.P,
-                                                                            kIrSlabs);
-    DASP_LAUNCH_OK("ir_grad_kernel");
+    ir_grad_pairs_kernel<<<dim3((unsigned)nbk, (unsigned)items), 256, 0, st>>>(ws_bpad, C, params + item0 * 25, ws_irpart,
+                                                                                g.L, g.leff, g.n2, nbk, nb, hop, P);
+    DASP_LAUNCH_OK("ir_grad_pairs_kernel");
     reverb_param_grad_kernel<<<(unsigned)((items * 25 + 127) / 128), 128, 0, st>>>(ws_irpart, ws_mixpart, params, gparams,
-                                                                                   item0, items, kIrSlabs, kMixBlocks);
+                                                                                   item0, items, nbk, kMixBlocks);
     DASP_LAUNCH_OK("reverb_param_grad_kernel");
   }
   return DASP_OK;

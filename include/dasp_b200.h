@@ -100,12 +100,14 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
  *        else the (bs*2, 12, num_samples + taps - 1) tensor the reference would have drawn
  *        (functional.py:547-548) -- the parity-test entry.
  * Buffers kept for the backward (pass NULL for all four when no backward follows):
- *   wet_save  bs*2*n floats, f_save  geom.f_floats floats (band-filtered noise blocks),
+ *   wet_save  bs*2*n floats, f_save  geom.f_floats floats (band-filtered noise blocks, left/right
+ *   channel interleaved as complex pairs),
  *   xspec_save / irspec_save  geom.spec_c64 complex64 each.
  * workspace: geom.fwd_workspace_bytes / geom.bwd_workspace_bytes bytes of device memory. */
 typedef struct dasp_reverb_geom {
-  int64_t nb, hop, nbk, ls;   /* overlap-save block length, hop, blocks and slot length per band signal */
-  int64_t n2;                 /* FFT length of the audio convolution (>= n + num_samples - 1, 7-smooth) */
+  int64_t nb, hop, nbk;       /* overlap-save block length, hop and blocks per band signal */
+  int64_t leff;               /* min(num_samples, n): IR taps that can reach the n output samples */
+  int64_t n2;                 /* FFT length of the audio convolution (>= n + leff - 1, 7-smooth) */
   int64_t chunk_items;        /* items processed per pass (L2-sized working set) */
   int64_t f_floats, spec_c64, wet_floats;
   int64_t fwd_workspace_bytes, bwd_workspace_bytes;
