@@ -387,9 +387,9 @@ def parametric_eq(
 
 import os as _os
 
-# items per pass of the reverb pipeline: small enough that the transient FFT buffers stay L2-resident
-# on B200, large enough to amortise launches (override for experiments with DASP_REVERB_CHUNK)
-REVERB_CHUNK_ITEMS = int(_os.environ.get("DASP_REVERB_CHUNK", "4"))
+# items per pass of the reverb pipeline (bounds the workspace; measured on B200: 8 -> 55 ms, 16 -> 42 ms,
+# 32 -> 34 ms per chain step at batch 1024; override for experiments with DASP_REVERB_CHUNK)
+REVERB_CHUNK_ITEMS = int(_os.environ.get("DASP_REVERB_CHUNK", "32"))
 
 
 class _ReverbFn(torch.autograd.Function):
