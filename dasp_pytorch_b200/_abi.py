@@ -51,7 +51,7 @@ _SIGNATURES = {
     "dasp_eq_bwd": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
     "dasp_reverb_geometry": (c_int, [I64, I64, I64, I64, I64, ctypes.POINTER(ReverbGeom)]),
     "dasp_reverb_fwd": (c_int, [P, I64, P, P, c_uint64, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, c_float, P]),
-    "dasp_reverb_bwd": (c_int, [P, P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, P]),
+    "dasp_reverb_bwd": (c_int, [P, P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P]),
     "dasp_reverb_filterbank": (c_int, [I64, c_double, ctypes.POINTER(c_float)]),
     "dasp_dynamics_tile_len": (I64, [I64, I64]),
     "dasp_dynamics_fwd": (c_int, [c_int, P, P, P, P, P, P, P, P, I64, I64, I64, c_float, c_float, I64, P]),

@@ -124,8 +124,13 @@ struct Geom {
   int64_t bs, n, L, taps, P;
   int64_t leff;                 // min(L, n): the only IR taps that can reach the output
   int64_t nb, hop, nbk, n2, chunk;
+  int64_t rpp;                  // polyphase factor of the spectral synthesis: n1 = rpp*nb >= leff + P
+  int64_t n1() const { return rpp * nb; }
+  int64_t n1c() const { return n1() / 2 + 1; }
   int64_t n2c() const { return n2 / 2 + 1; }
-  int64_t pair_c64() const { return nbk * nb; }          // complex samples per (item, band) pair
+  int64_t nparts_pp() const { return (nb + 255) / 256; }
+  // complex samples per (item, band) pair in either filtered-noise layout (overlap-save / polyphase)
+  int64_t pair_c64() const { return (nbk > rpp ? nbk : rpp) * nb; }
 };
 
 int make_geom(int64_t bs, int64_t n, int64_t L, int64_t taps, int64_t chunk, Geom& g) {
@@ -140,6 +145,7 @@ int make_geom(int64_t bs, int64_t n, int64_t L, int64_t taps, int64_t chunk, Geo
   g.hop = nb - discard;
   g.leff = L < n ? L : n;
   g.nbk = (g.leff + g.hop - 1) / g.hop;
+  g.rpp = (g.leff + g.P + nb - 1) / nb;
   g.n2 = next_conv_len(n + g.leff - 1);
   if (chunk <= 0) chunk = 4;
   g.chunk = chunk < bs ? chunk : (bs > 0 ? bs : 1);
@@ -155,7 +161,7 @@ struct PlanKey {
 };
 struct PlanVal { cufftHandle h; size_t work; };
 struct FbKey {
-  int dev; int64_t taps, nb; double sr;
+  int dev; int64_t taps, nb; double sr;      // nb < 0: half spectrum at n1 = -nb points (spectral synthesis)
   bool operator<(const FbKey& o) const { return std::tie(dev, taps, nb, sr) < std::tie(o.dev, o.taps, o.nb, o.sr); }
 };
 
@@ -239,6 +245,83 @@ __global__ void cmul_filter_pairs_kernel(float2* __restrict__ C, const float2* _
   }
 }
 
+// ---- spectral synthesis (device-noise mode) ------------------------------------------------------
+// The band-filtered noise only has to be a stationary Gaussian process with the FIR's autocovariance on
+// the window [0, leff).  A length-n1 PERIODIC white sequence filtered circularly has exactly that
+// covariance for every lag inside the window once n1 >= leff + P, and its spectrum has independent bins:
+//   G[j] = H_k[j] Z[j],  Z[j] ~ CN(0, n1)  (real N(0, n1) at j = 0 and n1/2),  G[n1-j] = conj(G[j]).
+// So the spectrum is drawn directly (no forward FFT, no separate filter pass) and only ONE inverse
+// transform remains.  n1 = R*nb is split Cooley-Tukey style so that the inverse is the fast single-kernel
+// nb-point batched C2C:   f[R a + b] = sum_{j1<nb} Q_b[j1] e^{2 pi i j1 a / nb},
+//   Q_b[j1] = e^{2 pi i j1 b / n1} * sum_{j2<R} G[j1 + nb j2] e^{2 pi i j2 b / R}
+// Polyphase layout: C[((item*12 + k)*R + b)*nb + a] = (f_left, f_right)[R a + b].
+// Left/right are packed as G_left + i G_right; one Philox call per canonical bin yields both channels.
+template <int R>
+__global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __restrict__ H1, int64_t item0, int nb,
+                                    unsigned long long seed) {
+  const int j1 = blockIdx.x * blockDim.x + threadIdx.x;       // residue class 0 .. nb/2
+  if (j1 > nb / 2) return;
+  const int k = blockIdx.y;
+  const int64_t il = blockIdx.z;
+  const int n1 = R * nb, n1h = n1 / 2;
+  const unsigned long long pair = (unsigned long long)((item0 + il) * kBands + k);
+  const float2* h = H1 + (int64_t)k * (n1h + 1);
+  const float s_half = sqrtf(0.5f * (float)n1), s_full = sqrtf((float)n1);
+
+  // value of the packed spectrum G_left + i G_right at bin j (0 <= j < n1) and at its mirror n1 - j
+  auto draw = [&](int j, float2& at_j, float2& at_mirror) {
+    const int jc = j <= n1h ? j : n1 - j;
+    curandStatePhilox4_32_10_t st;
+    curand_init(seed, (pair << 24) + (unsigned long long)jc, 0ull, &st);
+    const float4 z = curand_normal4(&st);
+    float2 zl, zr;
+    if (jc == 0 || jc == n1h) { zl = make_float2(z.x * s_full, 0.f); zr = make_float2(z.z * s_full, 0.f); }
+    else { zl = make_float2(z.x * s_half, z.y * s_half); zr = make_float2(z.z * s_half, z.w * s_half); }
+    const float2 w = h[jc];
+    const float2 sl = make_float2(w.x * zl.x - w.y * zl.y, w.x * zl.y + w.y * zl.x);   // H Z_left
+    const float2 sr = make_float2(w.x * zr.x - w.y * zr.y, w.x * zr.y + w.y * zr.x);   // H Z_right
+    const float2 canon = make_float2(sl.x - sr.y, sl.y + sr.x);      // S_l + i S_r           (bin jc)
+    const float2 mirr = make_float2(sl.x + sr.y, sr.x - sl.y);       // conj(S_l) + i conj(S_r) (bin n1 - jc)
+    if (j == jc) { at_j = canon; at_mirror = mirr; } else { at_j = mirr; at_mirror = canon; }
+  };
+
+  float2 ga[R], gb[R];
+  const bool self_mirror = (j1 == 0) || (2 * j1 == nb);     // class nb - j1 is class j1 itself
+#pragma unroll
+  for (int j2 = 0; j2 < R; ++j2) {
+    float2 a, m;
+    draw(j1 + nb * j2, a, m);
+    ga[j2] = a;
+    gb[R - 1 - j2] = m;          // mirror of bin j1 + nb j2 is bin (nb - j1) + nb (R-1-j2)
+  }
+  float2 root[R];
+#pragma unroll
+  for (int m = 0; m < R; ++m) sincospif(2.0f * (float)m / (float)R, &root[m].y, &root[m].x);
+  float2 w1a, w1b;
+  sincospif(2.0f * (float)j1 / (float)n1, &w1a.y, &w1a.x);
+  sincospif(2.0f * (float)(nb - j1) / (float)n1, &w1b.y, &w1b.x);
+  float2 twa = make_float2(1.f, 0.f), twb = make_float2(1.f, 0.f);
+  float2* outp = C + ((il * kBands + k) * R) * (int64_t)nb;
+#pragma unroll
+  for (int b = 0; b < R; ++b) {
+    float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int j2 = 0; j2 < R; ++j2) {
+      const float2 r = root[(j2 * b) % R];
+      sa.x = fmaf(ga[j2].x, r.x, fmaf(-ga[j2].y, r.y, sa.x));
+      sa.y = fmaf(ga[j2].x, r.y, fmaf(ga[j2].y, r.x, sa.y));
+      sb.x = fmaf(gb[j2].x, r.x, fmaf(-gb[j2].y, r.y, sb.x));
+      sb.y = fmaf(gb[j2].x, r.y, fmaf(gb[j2].y, r.x, sb.y));
+    }
+    outp[(int64_t)b * nb + j1] = make_float2(sa.x * twa.x - sa.y * twa.y, sa.x * twa.y + sa.y * twa.x);
+    if (!self_mirror)
+      outp[(int64_t)b * nb + (nb - j1)] = make_float2(sb.x * twb.x - sb.y * twb.y, sb.x * twb.y + sb.y * twb.x);
+    const float2 na = make_float2(twa.x * w1a.x - twa.y * w1a.y, twa.x * w1a.y + twa.y * w1a.x);
+    const float2 nbw = make_float2(twb.x * w1b.x - twb.y * w1b.y, twb.x * w1b.y + twb.y * w1b.x);
+    twa = na; twb = nbw;
+  }
+}
+
 // torch.linspace(0, 1, L) in fp32 (functional.py:561): symmetric fill around the midpoint
 __device__ __forceinline__ float time_axis(int64_t t, int64_t L, float step) {
   return (t < L / 2) ? step * (float)t : 1.0f - step * (float)(L - 1 - t);
@@ -277,6 +360,85 @@ __global__ void shape_ir_pairs_kernel(const float2* __restrict__ C, const float*
     }
     outl[t] = al;
     outr[t] = ar;
+  }
+}
+
+// polyphase layout variant: thread a handles times R a .. R a + R - 1 (irpad tail is pre-zeroed by memset)
+__global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __restrict__ params, float* __restrict__ irpad,
+                                   int64_t L, int64_t leff, int64_t n2, int R, int nb) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t il = blockIdx.y;
+  __shared__ float gk[kBands], rk[kBands];
+  if (threadIdx.x < kBands) {
+    gk[threadIdx.x] = params[il * 25 + threadIdx.x] * (1.0f / kBands);
+    rk[threadIdx.x] = -(params[il * 25 + kBands + threadIdx.x] * 10.0f + 1.0f);
+  }
+  __syncthreads();
+  if (a >= nb) return;
+  const float step = 1.0f / (float)(L - 1);
+  float* outl = irpad + (il * 2 + 0) * n2;
+  float* outr = irpad + (il * 2 + 1) * n2;
+  const float2* c0 = C + (il * kBands) * (int64_t)R * nb + a;
+  for (int ph = 0; ph < R; ++ph) {
+    const int64_t t = (int64_t)R * a + ph;
+    if (t >= leff) break;
+    const float tt = time_axis(t, L, step);
+    float al = 0.f, ar = 0.f;
+#pragma unroll
+    for (int k = 0; k < kBands; ++k) {
+      const float2 v = c0[((int64_t)k * R + ph) * nb];
+      const float e = gk[k] * expf(rk[k] * tt);
+      al = fmaf(e, v.x, al);
+      ar = fmaf(e, v.y, ar);
+    }
+    outl[t] = al;
+    outr[t] = ar;
+  }
+}
+
+// part[((item*nparts + blockIdx.x)*12 + k)*2 + {0,1}], nparts = gridDim.x
+__global__ void ir_grad_pp_kernel(const float* __restrict__ dir_pad, const float2* __restrict__ C,
+                                  const float* __restrict__ params, float* __restrict__ part, int64_t L, int64_t leff,
+                                  int64_t n2, int R, int nb) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t il = blockIdx.y;
+  __shared__ float rk[kBands];
+  __shared__ float red[8][2 * kBands];
+  if (threadIdx.x < kBands) rk[threadIdx.x] = -(params[il * 25 + kBands + threadIdx.x] * 10.0f + 1.0f);
+  __syncthreads();
+  const float step = 1.0f / (float)(L - 1);
+  const float* dl = dir_pad + (il * 2 + 0) * n2;
+  const float* dr = dir_pad + (il * 2 + 1) * n2;
+  float s0[kBands], s1[kBands];
+#pragma unroll
+  for (int k = 0; k < kBands; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
+  if (a < nb) {
+    const float2* c0 = C + (il * kBands) * (int64_t)R * nb + a;
+    for (int ph = 0; ph < R; ++ph) {
+      const int64_t t = (int64_t)R * a + ph;
+      if (t >= leff) break;
+      const float tt = time_axis(t, L, step);
+      const float gl = dl[t], gr = dr[t];
+#pragma unroll
+      for (int k = 0; k < kBands; ++k) {
+        const float2 v = c0[((int64_t)k * R + ph) * nb];
+        const float w = fmaf(gl, v.x, gr * v.y) * expf(rk[k] * tt);
+        s0[k] += w;
+        s1[k] = fmaf(w, tt, s1[k]);
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kBands; ++k) {
+    const float x0 = warp_sum(s0[k]), x1 = warp_sum(s1[k]);
+    if (lane == 0) { red[warp][2 * k] = x0; red[warp][2 * k + 1] = x1; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * kBands) {
+    float acc = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) acc += red[w][threadIdx.x];
+    part[((il * gridDim.x + blockIdx.x) * kBands) * 2 + threadIdx.x] = acc;
   }
 }
 
@@ -490,14 +652,71 @@ int get_filterbank(const Geom& g, double sr, cudaStream_t st, const float2** out
   return DASP_OK;
 }
 
-struct Plans { PlanVal blk_c2c, big_r2c, big_c2r; size_t work; };
+// half spectrum of the taps on the n1-point grid of the spectral synthesis: 12 x (n1/2+1) complex, scaled 1/n1
+int get_filterbank_n1(const Geom& g, double sr, cudaStream_t st, const float2** out) {
+  int dev = 0;
+  DASP_CUDA_OK(cudaGetDevice(&dev));
+  const int64_t n1 = g.n1(), n1c = g.n1c();
+  FbKey key{dev, g.taps, -n1, sr};
+  auto it = g_fb.find(key);
+  if (it != g_fb.end()) { *out = reinterpret_cast<const float2*>(it->second); return DASP_OK; }
+  DASP_REQUIRE(sr / 2.0 > 18000.0, "sample_rate %.1f too low: the filter bank needs 18 kHz < sr/2 (signal.py:84)", sr);
+  std::vector<float> taps;
+  octave_filterbank((int)g.taps, sr, taps);
+  std::vector<float> padded((size_t)kBands * n1, 0.f);
+  const float inv = 1.0f / (float)n1;
+  for (int k = 0; k < kBands; ++k)
+    for (int64_t i = 0; i < g.taps; ++i) padded[(size_t)k * n1 + i] = taps[(size_t)k * g.taps + i] * inv;
+  float* d_in = nullptr;
+  cufftComplex* d_out = nullptr;
+  void* d_work = nullptr;
+  DASP_CUDA_OK(cudaMalloc(&d_in, sizeof(float) * padded.size()));
+  DASP_CUDA_OK(cudaMalloc(&d_out, sizeof(cufftComplex) * kBands * n1c));
+  DASP_CUDA_OK(cudaMemcpyAsync(d_in, padded.data(), sizeof(float) * padded.size(), cudaMemcpyHostToDevice, st));
+  PlanVal pv;
+  int rc = get_plan(0, n1, kBands, n1, n1c, pv);
+  if (rc != DASP_OK) return rc;
+  DASP_CUDA_OK(cudaMalloc(&d_work, pv.work > 0 ? pv.work : 16));
+  DASP_CUFFT_OK(cufftSetStream(pv.h, st));
+  DASP_CUFFT_OK(cufftSetWorkArea(pv.h, d_work));
+  DASP_CUFFT_OK(cufftExecR2C(pv.h, d_in, d_out));
+  DASP_CUDA_OK(cudaStreamSynchronize(st));   // one-off cache fill
+  cudaFree(d_in);
+  cudaFree(d_work);
+  g_fb[key] = d_out;
+  *out = reinterpret_cast<const float2*>(d_out);
+  return DASP_OK;
+}
+
+template <int R>
+void launch_spectral(float2* C, const float2* H1, int64_t item0, int64_t items, int nb, unsigned long long seed,
+                     cudaStream_t st) {
+  const int threads = 128;
+  dim3 grid((unsigned)((nb / 2 + 1 + threads - 1) / threads), kBands, (unsigned)items);
+  spectral_gen_kernel<R><<<grid, threads, 0, st>>>(C, H1, item0, nb, seed);
+}
+bool dispatch_spectral(int R, float2* C, const float2* H1, int64_t item0, int64_t items, int nb,
+                       unsigned long long seed, cudaStream_t st) {
+  switch (R) {
+#define DASP_R(r) case r: launch_spectral<r>(C, H1, item0, items, nb, seed, st); return true;
+    DASP_R(1) DASP_R(2) DASP_R(3) DASP_R(4) DASP_R(5) DASP_R(6) DASP_R(7) DASP_R(8) DASP_R(9) DASP_R(10)
+    DASP_R(11) DASP_R(12) DASP_R(13) DASP_R(14) DASP_R(15) DASP_R(16)
+#undef DASP_R
+    default: return false;       // very long IRs fall back to the time-domain Philox + overlap-save path
+  }
+}
+constexpr int kMaxSpectralR = 16;
+
+struct Plans { PlanVal blk_c2c, pp_c2c, big_r2c, big_c2r; size_t work; };
 int get_plans(const Geom& g, int64_t items, Plans& p) {
   int rc;
   const int64_t nblocks = items * kBands * g.nbk;
   if ((rc = get_plan(2, g.nb, nblocks, g.nb, g.nb, p.blk_c2c)) != DASP_OK) return rc;
+  if ((rc = get_plan(2, g.nb, items * kBands * g.rpp, g.nb, g.nb, p.pp_c2c)) != DASP_OK) return rc;
   if ((rc = get_plan(0, g.n2, items * 2, g.n2, g.n2c(), p.big_r2c)) != DASP_OK) return rc;
   if ((rc = get_plan(1, g.n2, items * 2, g.n2c(), g.n2, p.big_c2r)) != DASP_OK) return rc;
   p.work = p.blk_c2c.work;
+  if (p.pp_c2c.work > p.work) p.work = p.pp_c2c.work;
   if (p.big_r2c.work > p.work) p.work = p.big_r2c.work;
   if (p.big_c2r.work > p.work) p.work = p.big_c2r.work;
   return DASP_OK;
@@ -529,7 +748,8 @@ void bwd_layout(const Geom& g, size_t cufft_work, BwdWs& w) {
   w.gspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
   w.aspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
   w.bspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
-  w.irpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * g.nbk * kBands * 2));
+  const int64_t nparts = g.nbk > g.nparts_pp() ? g.nbk : g.nparts_pp();
+  w.irpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * nparts * kBands * 2));
   w.mixpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * 2 * kMixBlocks));
   w.cufft = o; o += align256(cufft_work);
   w.total = o;
@@ -611,8 +831,10 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
   DASP_REQUIRE(x && params && y && workspace, "reverb fwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lk(g_mu);
-  const float2* H = nullptr;
-  if ((rc = get_filterbank(g, (double)sample_rate, st, &H)) != DASP_OK) return rc;
+  const float2 *H = nullptr, *H1 = nullptr;
+  const bool spectral = (noise == nullptr) && g.rpp <= kMaxSpectralR;
+  if (spectral) { if ((rc = get_filterbank_n1(g, (double)sample_rate, st, &H1)) != DASP_OK) return rc; }
+  else          { if ((rc = get_filterbank(g, (double)sample_rate, st, &H)) != DASP_OK) return rc; }
   Plans pfull{}, prem{};
   size_t work = 0;
   if ((rc = plans_for(g, pfull, prem, work)) != DASP_OK) return rc;
@@ -642,18 +864,32 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     const dim3 gblk((unsigned)nbk, kBands, (unsigned)items);
 
     // ---- IR synthesis ----
-    if (noise) noise_pairs_layout_kernel<<<gblk, 256, 0, st>>>(noise, C, item0, nbk, nb, hop, lp);
-    else       noise_pairs_philox_kernel<<<gblk, 256, 0, st>>>(C, item0, nbk, nb, hop, (unsigned long long)seed);
-    DASP_LAUNCH_OK("reverb noise kernel");
-    DASP_CUFFT_OK(cufftSetStream(pl.blk_c2c.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.blk_c2c.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecC2C(pl.blk_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_FORWARD));
-    cmul_filter_pairs_kernel<<<gblk, 256, 0, st>>>(C, H, nbk, nb);
-    DASP_LAUNCH_OK("cmul_filter_pairs_kernel");
-    DASP_CUFFT_OK(cufftExecC2C(pl.blk_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_INVERSE));
-    shape_ir_pairs_kernel<<<dim3((unsigned)((g.n2 + hop - 1) / hop), (unsigned)items), 256, 0, st>>>(
-        C, params + item0 * 25, ws_irpad, g.L, g.leff, g.n2, nbk, nb, hop, P);
-    DASP_LAUNCH_OK("shape_ir_pairs_kernel");
+    if (!noise && g.rpp <= kMaxSpectralR) {
+      // device noise: draw the filtered spectrum directly, one inverse transform (polyphase layout)
+      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, (unsigned long long)seed, st);
+      DASP_LAUNCH_OK("spectral_gen_kernel");
+      DASP_CUFFT_OK(cufftSetStream(pl.pp_c2c.h, st));
+      DASP_CUFFT_OK(cufftSetWorkArea(pl.pp_c2c.h, ws_cufft));
+      DASP_CUFFT_OK(cufftExecC2C(pl.pp_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_INVERSE));
+      DASP_CUDA_OK(cudaMemsetAsync(ws_irpad, 0, sizeof(float) * rows * g.n2, st));
+      shape_ir_pp_kernel<<<dim3((unsigned)g.nparts_pp(), (unsigned)items), 256, 0, st>>>(
+          C, params + item0 * 25, ws_irpad, g.L, g.leff, g.n2, (int)g.rpp, nb);
+      DASP_LAUNCH_OK("shape_ir_pp_kernel");
+    } else {
+      // parity mode (caller's noise tensor) or very long IR: time-domain noise, overlap-save blocks
+      if (noise) noise_pairs_layout_kernel<<<gblk, 256, 0, st>>>(noise, C, item0, nbk, nb, hop, lp);
+      else       noise_pairs_philox_kernel<<<gblk, 256, 0, st>>>(C, item0, nbk, nb, hop, (unsigned long long)seed);
+      DASP_LAUNCH_OK("reverb noise kernel");
+      DASP_CUFFT_OK(cufftSetStream(pl.blk_c2c.h, st));
+      DASP_CUFFT_OK(cufftSetWorkArea(pl.blk_c2c.h, ws_cufft));
+      DASP_CUFFT_OK(cufftExecC2C(pl.blk_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_FORWARD));
+      cmul_filter_pairs_kernel<<<gblk, 256, 0, st>>>(C, H, nbk, nb);
+      DASP_LAUNCH_OK("cmul_filter_pairs_kernel");
+      DASP_CUFFT_OK(cufftExecC2C(pl.blk_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_INVERSE));
+      shape_ir_pairs_kernel<<<dim3((unsigned)((g.n2 + hop - 1) / hop), (unsigned)items), 256, 0, st>>>(
+          C, params + item0 * 25, ws_irpad, g.L, g.leff, g.n2, nbk, nb, hop, P);
+      DASP_LAUNCH_OK("shape_ir_pairs_kernel");
+    }
 
     // ---- apply ----
     pad_x_kernel<<<grid_for(rows * g.n2), 256, 0, st>>>(x, ws_xpad, item0, rows, n, g.n2, (int)in_chs);
@@ -676,12 +912,13 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
 int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float* params, const float* wet_save,
                     const float* f_save, const void* xspec_save, const void* irspec_save, float* gx, float* gparams,
                     void* workspace, int64_t workspace_bytes, int64_t bs, int64_t n, int64_t num_samples, int64_t taps,
-                    int64_t chunk_items, void* stream) {
+                    int64_t chunk_items, int64_t device_noise, void* stream) {
   Geom g;
   int rc = make_geom(bs, n, num_samples, taps, chunk_items, g);
   if (rc != DASP_OK) return rc;
   DASP_REQUIRE(in_chs == 1 || in_chs == 2, "only mono/stereo signals are supported");
   if (bs == 0) return DASP_OK;
+  const bool polyphase = device_noise != 0 && g.rpp <= kMaxSpectralR;   // layout the forward left in f_save
   DASP_REQUIRE(gy && x && params && wet_save && f_save && xspec_save && irspec_save && gx && gparams && workspace,
                "reverb bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
@@ -731,11 +968,19 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
     finish_dx_kernel<<<grid_for(items * in_chs * n), 256, 0, st>>>(gy, ws_gpad, params, gx, item0, items, n, g.n2,
                                                                    (int)in_chs);
     DASP_LAUNCH_OK("finish_dx_kernel");
-    ir_grad_pairs_kernel<<<dim3((unsigned)nbk, (unsigned)items), 256, 0, st>>>(ws_bpad, C, params + item0 * 25, ws_irpart,
-                                                                                g.L, g.leff, g.n2, nbk, nb, hop, P);
-    DASP_LAUNCH_OK("ir_grad_pairs_kernel");
+    int nparts;
+    if (polyphase) {
+      nparts = (int)g.nparts_pp();
+      ir_grad_pp_kernel<<<dim3((unsigned)nparts, (unsigned)items), 256, 0, st>>>(ws_bpad, C, params + item0 * 25, ws_irpart,
+                                                                                g.L, g.leff, g.n2, (int)g.rpp, nb);
+    } else {
+      nparts = nbk;
+      ir_grad_pairs_kernel<<<dim3((unsigned)nbk, (unsigned)items), 256, 0, st>>>(ws_bpad, C, params + item0 * 25, ws_irpart,
+                                                                                  g.L, g.leff, g.n2, nbk, nb, hop, P);
+    }
+    DASP_LAUNCH_OK("ir_grad kernel");
     reverb_param_grad_kernel<<<(unsigned)((items * 25 + 127) / 128), 128, 0, st>>>(ws_irpart, ws_mixpart, params, gparams,
-                                                                                   item0, items, nbk, kMixBlocks);
+                                                                                   item0, items, nparts, kMixBlocks);
     DASP_LAUNCH_OK("reverb_param_grad_kernel");
   }
   return DASP_OK;

@@ -418,14 +418,14 @@ class _ReverbFn(torch.autograd.Function):
                                           taps, chunk, float(sample_rate), stream_ptr(dev)), "dasp_reverb_fwd")
         if need_bwd:
             ctx.save_for_backward(x, params, wet, fsave, xspec, irspec)
-        ctx.cfg = (num_samples, taps, chunk, geom.bwd_workspace_bytes)
+        ctx.cfg = (num_samples, taps, chunk, geom.bwd_workspace_bytes, 1 if noise is None else 0)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         lib = _abi.lib()
         x, params, wet, fsave, xspec, irspec = ctx.saved_tensors
-        num_samples, taps, chunk, bwd_bytes = ctx.cfg
+        num_samples, taps, chunk, bwd_bytes, device_noise = ctx.cfg
         bs, in_chs, n = x.shape
         dev = x.device
         gy = gy.contiguous()
@@ -435,7 +435,7 @@ class _ReverbFn(torch.autograd.Function):
         with torch.cuda.device(dev), _timed("reverb_bwd", dev):
             check(lib.dasp_reverb_bwd(ptr(gy), ptr(x), in_chs, ptr(params), ptr(wet), ptr(fsave), ptr(xspec),
                                       ptr(irspec), ptr(gx), ptr(gp), ptr(ws), ws.numel(), bs, n, num_samples, taps,
-                                      chunk, stream_ptr(dev)), "dasp_reverb_bwd")
+                                      chunk, device_noise, stream_ptr(dev)), "dasp_reverb_bwd")
         return gx, gp, None, None, None, None, None, None
 
 

@@ -122,7 +122,8 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
                     const float* wet_save, const float* f_save, const void* xspec_save,
                     const void* irspec_save, float* gx, float* gparams, void* workspace,
                     int64_t workspace_bytes, int64_t bs, int64_t n, int64_t num_samples, int64_t taps,
-                    int64_t chunk_items, void* stream);
+                    int64_t chunk_items, int64_t device_noise /* 1 iff the forward ran with noise == NULL */,
+                    void* stream);
 /* host-only: the 12 x taps fp32 filter bank (scipy.signal.firwin restated; no GPU needed) */
 int dasp_reverb_filterbank(int64_t taps, double sample_rate, float* out);
 

@@ -103,6 +103,40 @@ def test_reverb_device_noise_properties(cuda_device):
     assert (ir[:, 0] - ir[:, 1]).abs().max() > 1e-4
 
 
+def test_reverb_device_noise_band_statistics(cuda_device):
+    """spectral synthesis (device noise) must produce an IR with the same second-order statistics as the
+    reference construction: compare octave-band energies of the IR, averaged over 24 items x 2 channels,
+    with the oracle fed reference-style time-domain noise."""
+    import dasp_pytorch_b200 as D
+    bs, n, L, taps = 24, 48000, 96000, 1023            # BASELINE geometry: leff = 48000, polyphase factor 6
+    x = torch.zeros(bs, 2, n, device=cuda_device)
+    x[:, :, 0] = 1.0
+    ones = torch.ones(bs, device=cuda_device)
+    p = [ones * 1.0] * 12 + [ones * 0.3] * 12 + [ones]
+    torch.manual_seed(7)
+    ir = D.noise_shaped_reverberation(x, SR, *p, num_samples=L, num_bandpass_taps=taps).cpu().double()
+    nref = 6
+    noise = oracle.reverb_noise(nref, L, taps, 11)
+    ref = oracle.noise_shaped_reverberation(x[:nref].cpu().double(), SR, *[q[:nref].cpu().double() for q in p],
+                                            num_samples=L, num_bandpass_taps=taps, noise=noise)
+    edges = [0, 22, 45, 90, 180, 355, 710, 1400, 2800, 5600, 11200, 17000, 22050]
+    freqs = torch.fft.rfftfreq(n, 1 / SR)
+
+    def band_energy(sig):
+        pw = torch.fft.rfft(sig, dim=-1).abs().pow(2).mean(dim=(0, 1))
+        return torch.stack([pw[(freqs >= lo) & (freqs < hi)].sum() for lo, hi in zip(edges[:-1], edges[1:])])
+
+    e_new, e_ref = band_energy(ir), band_energy(ref)
+    ratio = e_new / e_ref
+    assert ((ratio > 0.55) & (ratio < 1.8)).all(), ratio        # few independent draws in the lowest bands
+    assert abs(float(ratio[4:].log().mean())) < 0.12, ratio     # well-averaged bands agree within ~10 %
+    # envelope: energy of the last quarter relative to the first quarter follows exp(-2 (10*0.3+1) t)
+    q = n // 4
+    dec_new = ir[..., -q:].pow(2).sum() / ir[..., :q].pow(2).sum()
+    dec_ref = ref[..., -q:].pow(2).sum() / ref[..., :q].pow(2).sum()
+    assert 0.7 < float(dec_new / dec_ref) < 1.4
+
+
 def test_reverb_contract(cuda_device):
     import dasp_pytorch_b200 as D
     x = torch.rand(2, 2, 512, device=cuda_device)
