@@ -337,7 +337,7 @@ def main():
                         "unit": "GB/s", "frac": breakdown[dom]["frac"], "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": breakdown[dom]["ms"]}
         chunks = -(-bs // F.REVERB_CHUNK_ITEMS)
-        own_launches_per_step = 1 + 2 + 1 + 1 + 1 + 2 + chunks * (6 + 6)
+        own_launches_per_step = 1 + 2 + 1 + 1 + 1 + 2 + chunks * (5 + 6)   # eq f/b, comp f/b, dist f/b, reverb per chunk
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -28,8 +28,8 @@ class ReverbGeom(ctypes.Structure):
     """mirror of ``dasp_reverb_geom`` (include/dasp_b200.h)"""
 
     _fields_ = [(name, c_int64) for name in (
-        "nb", "hop", "nbk", "leff", "n2", "chunk_items", "f_floats", "spec_c64", "wet_floats",
-        "fwd_workspace_bytes", "bwd_workspace_bytes")]
+        "nb", "hop", "nbk", "leff", "rpp", "conv_block", "x_blocks", "ir_partitions", "chunk_items",
+        "f_floats", "xspec_c64", "irspec_c64", "wet_floats", "fwd_workspace_bytes", "bwd_workspace_bytes")]
 
 P = c_void_p       # device pointer
 I64 = c_int64

@@ -42,6 +42,8 @@ namespace dasp {
 namespace {
 
 constexpr int kBands = 12;
+constexpr int kB = 4096;          // partition / hop of the audio convolution
+constexpr int kNbA = 2 * kB;      // its FFT length (single-kernel cuFFT C2C size)
 constexpr int kSig = 2 * kBands;     // band signals per item (stereo)
 constexpr double kPi = 3.14159265358979323846;
 
@@ -123,11 +125,11 @@ int64_t next_conv_len(int64_t v) {
 struct Geom {
   int64_t bs, n, L, taps, P;
   int64_t leff;                 // min(L, n): the only IR taps that can reach the output
-  int64_t nb, hop, nbk, n2, chunk;
+  int64_t nb, hop, nbk, chunk;
+  int64_t ib, jb;               // audio convolution: output/input blocks of kB samples, IR partitions of kB taps
   int64_t rpp;                  // polyphase factor of the spectral synthesis: n1 = rpp*nb >= leff + P
   int64_t n1() const { return rpp * nb; }
   int64_t n1c() const { return n1() / 2 + 1; }
-  int64_t n2c() const { return n2 / 2 + 1; }
   int64_t nparts_pp() const { return (nb + 255) / 256; }
   // complex samples per (item, band) pair in either filtered-noise layout (overlap-save / polyphase)
   int64_t pair_c64() const { return (nbk > rpp ? nbk : rpp) * nb; }
@@ -146,7 +148,8 @@ int make_geom(int64_t bs, int64_t n, int64_t L, int64_t taps, int64_t chunk, Geo
   g.leff = L < n ? L : n;
   g.nbk = (g.leff + g.hop - 1) / g.hop;
   g.rpp = (g.leff + g.P + nb - 1) / nb;
-  g.n2 = next_conv_len(n + g.leff - 1);
+  g.ib = (n + kB - 1) / kB;
+  g.jb = (g.leff + kB - 1) / kB;
   if (chunk <= 0) chunk = 4;
   g.chunk = chunk < bs ? chunk : (bs > 0 ? bs : 1);
   return DASP_OK;
@@ -327,10 +330,11 @@ __device__ __forceinline__ float time_axis(int64_t t, int64_t L, float step) {
   return (t < L / 2) ? step * (float)t : 1.0f - step * (float)(L - 1 - t);
 }
 
-// IR[c][t] = (1/12) sum_k gain_k exp(-(10 decay_k + 1) tt(t)) f_c[k][t]  for t < leff, zero up to n2.
-// grid = (ceil(n2 / hop), items): CTA (b, item) writes samples [b*hop, (b+1)*hop) of both channel rows.
+// IR[c][t] = (1/12) sum_k gain_k exp(-(10 decay_k + 1) tt(t)) f_c[k][t]  for t < leff, written as (left, right)
+// complex pairs into the zero-initialised partition layout of the audio convolution.
+// grid = (nbk, items): CTA (b, item) produces samples [b*hop, (b+1)*hop).
 __global__ void shape_ir_pairs_kernel(const float2* __restrict__ C, const float* __restrict__ params /* chunk x 25 */,
-                                      float* __restrict__ irpad, int64_t L, int64_t leff, int64_t n2, int nbk, int nb,
+                                      float2* __restrict__ Hb, int64_t L, int64_t leff, int jb, int nbk, int nb,
                                       int hop, int P) {
   const int b = blockIdx.x;
   const int64_t il = blockIdx.y;
@@ -341,31 +345,27 @@ __global__ void shape_ir_pairs_kernel(const float2* __restrict__ C, const float*
   }
   __syncthreads();
   const float step = 1.0f / (float)(L - 1);
-  float* outl = irpad + (il * 2 + 0) * n2;
-  float* outr = irpad + (il * 2 + 1) * n2;
+  float2* out = Hb + il * (int64_t)jb * kNbA;      // partition j holds taps [j kB, (j+1) kB) in its first half
   for (int m = threadIdx.x; m < hop; m += blockDim.x) {
     const int64_t t = (int64_t)b * hop + m;
-    if (t >= n2) break;
+    if (t >= leff) break;
+    const float tt = time_axis(t, L, step);
+    const float2* c = C + ((il * kBands) * nbk + b) * (int64_t)nb + m + P;
     float al = 0.f, ar = 0.f;
-    if (t < leff) {
-      const float tt = time_axis(t, L, step);
-      const float2* c = C + ((il * kBands) * nbk + b) * (int64_t)nb + m + P;
 #pragma unroll
-      for (int k = 0; k < kBands; ++k) {
-        const float2 v = c[(int64_t)k * nbk * nb];
-        const float e = gk[k] * expf(rk[k] * tt);
-        al = fmaf(e, v.x, al);
-        ar = fmaf(e, v.y, ar);
-      }
+    for (int k = 0; k < kBands; ++k) {
+      const float2 v = c[(int64_t)k * nbk * nb];
+      const float e = gk[k] * expf(rk[k] * tt);
+      al = fmaf(e, v.x, al);
+      ar = fmaf(e, v.y, ar);
     }
-    outl[t] = al;
-    outr[t] = ar;
+    out[(t / kB) * kNbA + (t % kB)] = make_float2(al, ar);
   }
 }
 
 // polyphase layout variant: thread a handles times R a .. R a + R - 1 (irpad tail is pre-zeroed by memset)
-__global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __restrict__ params, float* __restrict__ irpad,
-                                   int64_t L, int64_t leff, int64_t n2, int R, int nb) {
+__global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __restrict__ params, float2* __restrict__ Hb,
+                                   int64_t L, int64_t leff, int jb, int R, int nb) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t il = blockIdx.y;
   __shared__ float gk[kBands], rk[kBands];
@@ -376,8 +376,7 @@ __global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __
   __syncthreads();
   if (a >= nb) return;
   const float step = 1.0f / (float)(L - 1);
-  float* outl = irpad + (il * 2 + 0) * n2;
-  float* outr = irpad + (il * 2 + 1) * n2;
+  float2* out = Hb + il * (int64_t)jb * kNbA;
   const float2* c0 = C + (il * kBands) * (int64_t)R * nb + a;
   for (int ph = 0; ph < R; ++ph) {
     const int64_t t = (int64_t)R * a + ph;
@@ -391,15 +390,14 @@ __global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __
       al = fmaf(e, v.x, al);
       ar = fmaf(e, v.y, ar);
     }
-    outl[t] = al;
-    outr[t] = ar;
+    out[(t / kB) * kNbA + (t % kB)] = make_float2(al, ar);
   }
 }
 
 // part[((item*nparts + blockIdx.x)*12 + k)*2 + {0,1}], nparts = gridDim.x
-__global__ void ir_grad_pp_kernel(const float* __restrict__ dir_pad, const float2* __restrict__ C,
+__global__ void ir_grad_pp_kernel(const float2* __restrict__ Et, const float2* __restrict__ C,
                                   const float* __restrict__ params, float* __restrict__ part, int64_t L, int64_t leff,
-                                  int64_t n2, int R, int nb) {
+                                  int jb, int R, int nb) {
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t il = blockIdx.y;
   __shared__ float rk[kBands];
@@ -407,8 +405,7 @@ __global__ void ir_grad_pp_kernel(const float* __restrict__ dir_pad, const float
   if (threadIdx.x < kBands) rk[threadIdx.x] = -(params[il * 25 + kBands + threadIdx.x] * 10.0f + 1.0f);
   __syncthreads();
   const float step = 1.0f / (float)(L - 1);
-  const float* dl = dir_pad + (il * 2 + 0) * n2;
-  const float* dr = dir_pad + (il * 2 + 1) * n2;
+  const float2* de = Et + il * (int64_t)jb * kNbA;       // dL/dIR (left, right) in the first half of partition t/kB
   float s0[kBands], s1[kBands];
 #pragma unroll
   for (int k = 0; k < kBands; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
@@ -418,7 +415,8 @@ __global__ void ir_grad_pp_kernel(const float* __restrict__ dir_pad, const float
       const int64_t t = (int64_t)R * a + ph;
       if (t >= leff) break;
       const float tt = time_axis(t, L, step);
-      const float gl = dl[t], gr = dr[t];
+      const float2 gd = de[(t / kB) * kNbA + (t % kB)];
+      const float gl = gd.x, gr = gd.y;
 #pragma unroll
       for (int k = 0; k < kBands; ++k) {
         const float2 v = c0[((int64_t)k * R + ph) * nb];
@@ -442,112 +440,193 @@ __global__ void ir_grad_pp_kernel(const float* __restrict__ dir_pad, const float
   }
 }
 
-// xpad[r][t] = x[b, c (or 0 if mono), t] for t < n, else 0
-__global__ void pad_x_kernel(const float* __restrict__ x, float* __restrict__ xpad, int64_t item0, int64_t rows,
-                             int64_t n, int64_t n2, int in_chs) {
-  const int64_t total = rows * n2;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / n2, t = i - r * n2;
-    float v = 0.f;
-    if (t < n) {
-      const int64_t b = item0 + (r >> 1);
-      const int c = in_chs == 1 ? 0 : (int)(r & 1);
-      v = x[(b * in_chs + c) * n + t];
+// ---- audio convolution: uniformly partitioned overlap-save in the frequency domain -----------------
+// y[n] = sum_{t<=n} IR[t] x[n-t] (n < N) with the IR split into J partitions of kB taps and the audio into
+// I blocks of kB samples; every transform is the fast single-kernel kNbA-point batched C2C, with the LEFT
+// and RIGHT channel packed as real/imag (the channels have different IRs, so the multiply kernels untangle
+// the packed spectra through their Hermitian symmetry and re-pack the products).
+//   Xs[i] = FFT(x window [(i-1) kB, (i+1) kB)),  Hs[j] = FFT(IR[j kB, (j+1) kB) zero padded)
+//   y block i = last kB samples of IFFT(sum_{j<=i} Xs[i-j] Hs[j]) / kNbA
+// Backward: Gs[i] = FFT(mix g block i, in the second half), dx windows = IFFT(sum_j conj(Hs[j]) Gs[q+j]),
+//   dIR partition j = first kB samples of IFFT(sum_i conj(Xs[i-j]) Gs[i]).
+
+// Xb[(il*I + i)*kNbA + m] = (x_left, x_right)[(i-1) kB + m]
+__global__ void x_blocks_kernel(const float* __restrict__ x, float2* __restrict__ Xb, int64_t item0, int I, int64_t n,
+                                int in_chs) {
+  const int i = blockIdx.x;
+  const int64_t il = blockIdx.y;
+  const float* xl = x + ((item0 + il) * in_chs) * n;
+  const float* xr = in_chs == 1 ? xl : xl + n;
+  float2* out = Xb + (il * I + i) * (int64_t)kNbA;
+  for (int m = threadIdx.x; m < kNbA; m += blockDim.x) {
+    const int64_t idx = (int64_t)(i - 1) * kB + m;
+    float2 v = make_float2(0.f, 0.f);
+    if (idx >= 0 && idx < n) v = make_float2(xl[idx], xr[idx]);
+    out[m] = v;
+  }
+}
+
+// packed spectrum of (a + i b), a and b real: A[f] = (Z[f] + conj(Z[-f]))/2, B[f] = (Z[f] - conj(Z[-f]))/(2i)
+__device__ __forceinline__ void untangle(float2 z, float2 zm, float2& a, float2& b) {
+  a = make_float2(0.5f * (z.x + zm.x), 0.5f * (z.y - zm.y));
+  b = make_float2(0.5f * (z.y + zm.y), -0.5f * (z.x - zm.x));
+}
+__device__ __forceinline__ void cfma(float2& acc, float2 p, float2 q) {          // acc += p q
+  acc.x = fmaf(p.x, q.x, fmaf(-p.y, q.y, acc.x));
+  acc.y = fmaf(p.x, q.y, fmaf(p.y, q.x, acc.y));
+}
+__device__ __forceinline__ void cfma_conj(float2& acc, float2 p, float2 q) {     // acc += p conj(q)
+  acc.x = fmaf(p.x, q.x, fmaf(p.y, q.y, acc.x));
+  acc.y = fmaf(p.y, q.x, fmaf(-p.x, q.y, acc.y));
+}
+
+// CORR == false: out[o] = sum_{j<nbm, j<=o} A[o-j] B[j]           (o < nout)      forward
+// CORR == true : out[o] = sum_{j<nbm, o+j<na} A[o+j] conj(B[j])   (o < nout)      both backward products
+// A: [items][na][kNbA], Bm: [items][nbm][kNbA], Out: [items][nout][kNbA]; per channel, packed spectra.
+// grid = (ceil((kNbA/2+1)/128), items); thread = frequency pair (f, kNbA - f).  MAXB > 0: operands cached
+// in registers (na, nbm <= MAXB); MAXB == 0: generic loop straight from L2.
+template <int MAXB, bool CORR>
+__global__ void __launch_bounds__(128) partition_mac_kernel(const float2* __restrict__ A, const float2* __restrict__ Bm,
+                                                            float2* __restrict__ Out, int na, int nbm, int nout,
+                                                            float scale) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > kNbA / 2) return;
+  const int fm = (kNbA - f) & (kNbA - 1);
+  const int64_t il = blockIdx.y;
+  const float2* a = A + il * (int64_t)na * kNbA;
+  const float2* bq = Bm + il * (int64_t)nbm * kNbA;
+  float2* out = Out + il * (int64_t)nout * kNbA;
+  auto emit = [&](int o, float2 sl, float2 sr) {
+    sl.x *= scale; sl.y *= scale; sr.x *= scale; sr.y *= scale;
+    out[(int64_t)o * kNbA + f] = make_float2(sl.x - sr.y, sl.y + sr.x);                 // L + i R
+    if (fm != f) out[(int64_t)o * kNbA + fm] = make_float2(sl.x + sr.y, sr.x - sl.y);   // conj(L) + i conj(R)
+  };
+  if constexpr (MAXB > 0) {
+    float2 al[MAXB], ar[MAXB], bl[MAXB], br[MAXB];
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) {
+      al[i] = ar[i] = bl[i] = br[i] = make_float2(0.f, 0.f);      // operands beyond na / nbm are zero
+      if (i < na) untangle(a[(int64_t)i * kNbA + f], a[(int64_t)i * kNbA + fm], al[i], ar[i]);
+      if (i < nbm) untangle(bq[(int64_t)i * kNbA + f], bq[(int64_t)i * kNbA + fm], bl[i], br[i]);
     }
-    xpad[i] = v;
+#pragma unroll
+    for (int o = 0; o < MAXB; ++o) {
+      if (o < nout) {
+        float2 sl = make_float2(0.f, 0.f), sr = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < MAXB; ++j) {
+          const int ia = CORR ? o + j : o - j;                       // compile-time after unrolling
+          if (ia >= 0 && ia < MAXB) {
+            if (CORR) { cfma_conj(sl, al[ia], bl[j]); cfma_conj(sr, ar[ia], br[j]); }
+            else      { cfma(sl, al[ia], bl[j]); cfma(sr, ar[ia], br[j]); }
+          }
+        }
+        emit(o, sl, sr);
+      }
+    }
+  } else {
+    for (int o = 0; o < nout; ++o) {
+      float2 sl = make_float2(0.f, 0.f), sr = make_float2(0.f, 0.f);
+      for (int j = 0; j < nbm; ++j) {
+        const int ia = CORR ? o + j : o - j;
+        if (ia < 0 || ia >= na) continue;
+        float2 pl, pr, ql, qr;
+        untangle(a[(int64_t)ia * kNbA + f], a[(int64_t)ia * kNbA + fm], pl, pr);
+        untangle(bq[(int64_t)j * kNbA + f], bq[(int64_t)j * kNbA + fm], ql, qr);
+        if (CORR) { cfma_conj(sl, pl, ql); cfma_conj(sr, pr, qr); }
+        else      { cfma(sl, pl, ql); cfma(sr, pr, qr); }
+      }
+      emit(o, sl, sr);
+    }
   }
 }
 
-// out = a * b * scale            (CONJ == false)
-// out = a * conj(b) * scale      (CONJ == true)
-template <bool CONJ>
-__global__ void cmul_kernel(const cufftComplex* __restrict__ a, const cufftComplex* __restrict__ b,
-                            cufftComplex* __restrict__ out, int64_t total, float scale) {
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const cufftComplex p = a[i], q = b[i];
-    const float qi = CONJ ? -q.y : q.y;
-    out[i] = make_cuFloatComplex((p.x * q.x - p.y * qi) * scale, (p.x * qi + p.y * q.x) * scale);
-  }
-}
-
-// y = (1-mix) x + mix wet, wet = ypad[:, :n];  also saves wet for the backward (may be null)
-__global__ void mix_kernel(const float* __restrict__ x, const float* __restrict__ ypad, const float* __restrict__ params,
-                           float* __restrict__ y, float* __restrict__ wet_save, int64_t item0, int64_t rows, int64_t n,
-                           int64_t n2, int in_chs) {
-  const int64_t total = rows * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = i / n, t = i - r * n;
-    const int64_t b = item0 + (r >> 1);
-    const int c = in_chs == 1 ? 0 : (int)(r & 1);
-    const float mix = params[b * 25 + 24];
-    const float xv = x[(b * in_chs + c) * n + t];
-    const float wv = ypad[r * n2 + t];
-    const int64_t o = (item0 * 2 + r) * n + t;
-    y[o] = fmaf(mix, wv - xv, xv);            // (1-mix) x + mix wet
-    if (wet_save) wet_save[o] = wv;
-  }
-}
-
-// backward: gpad[r][t] = mix * gy[b, c, t] (zero padded), and per-(row, block) partial of sum gy (wet - x)
-__global__ void pad_g_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ wet,
-                             const float* __restrict__ params, float* __restrict__ gpad, float* __restrict__ mix_part,
-                             int64_t item0, int64_t n, int64_t n2, int in_chs) {
-  // grid = (blocks_per_row, rows)
-  const int64_t r = blockIdx.y;
-  const int64_t b = item0 + (r >> 1);
-  const int c = in_chs == 1 ? 0 : (int)(r & 1);
+// y = (1-mix) x + mix wet; wet[n] = Yt[(il*I + n/kB)*kNbA + kB + n%kB]; also saves wet for the backward
+__global__ void mix_blocks_kernel(const float* __restrict__ x, const float2* __restrict__ Yt,
+                                  const float* __restrict__ params, float* __restrict__ y, float* __restrict__ wet_save,
+                                  int64_t item0, int I, int64_t n, int in_chs) {
+  const int i = blockIdx.x;
+  const int64_t il = blockIdx.y, b = item0 + il;
   const float mix = params[b * 25 + 24];
-  const float* gr = gy + (item0 * 2 + r) * n;
-  const float* wr = wet + (item0 * 2 + r) * n;
-  const float* xr = x + (b * in_chs + c) * n;
+  const float* xl = x + (b * in_chs) * n;
+  const float* xr = in_chs == 1 ? xl : xl + n;
+  const float2* yt = Yt + (il * I + i) * (int64_t)kNbA + kB;
+  for (int m = threadIdx.x; m < kB; m += blockDim.x) {
+    const int64_t t = (int64_t)i * kB + m;
+    if (t >= n) break;
+    const float2 w = yt[m];
+    const float a0 = xl[t], a1 = xr[t];
+    y[(b * 2 + 0) * n + t] = fmaf(mix, w.x - a0, a0);
+    y[(b * 2 + 1) * n + t] = fmaf(mix, w.y - a1, a1);
+    if (wet_save) { wet_save[(b * 2 + 0) * n + t] = w.x; wet_save[(b * 2 + 1) * n + t] = w.y; }
+  }
+}
+
+// backward: Gb[(il*I + i)*kNbA + kB + m] = mix (g_left, g_right)[i kB + m], first half zero;
+// mix_part[il*I + i] = sum over the block and both channels of g (wet - x)
+__global__ void g_blocks_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ wet,
+                                const float* __restrict__ params, float2* __restrict__ Gb, float* __restrict__ mix_part,
+                                int64_t item0, int I, int64_t n, int in_chs) {
+  const int i = blockIdx.x;
+  const int64_t il = blockIdx.y, b = item0 + il;
+  const float mix = params[b * 25 + 24];
+  const float* xl = x + (b * in_chs) * n;
+  const float* xr = in_chs == 1 ? xl : xl + n;
+  const float* gl = gy + (b * 2 + 0) * n;
+  const float* gr = gy + (b * 2 + 1) * n;
+  const float* wl = wet + (b * 2 + 0) * n;
+  const float* wr = wet + (b * 2 + 1) * n;
+  float2* out = Gb + (il * I + i) * (int64_t)kNbA;
   float acc = 0.f;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n2; t += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.f;
+  for (int m = threadIdx.x; m < kB; m += blockDim.x) {
+    const int64_t t = (int64_t)i * kB + m;
+    float2 v = make_float2(0.f, 0.f);
     if (t < n) {
-      const float g = gr[t];
-      v = mix * g;
-      acc = fmaf(g, wr[t] - xr[t], acc);
+      const float g0 = gl[t], g1 = gr[t];
+      v = make_float2(mix * g0, mix * g1);
+      acc = fmaf(g0, wl[t] - xl[t], fmaf(g1, wr[t] - xr[t], acc));
     }
-    gpad[r * n2 + t] = v;
+    out[m] = make_float2(0.f, 0.f);
+    out[kB + m] = v;
   }
   __shared__ float wp[32];
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) wp[threadIdx.x >> 5] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += wp[w];
-    mix_part[r * gridDim.x + blockIdx.x] = s;
+    float sum = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += wp[w];
+    mix_part[il * I + i] = sum;
   }
 }
 
-// gx = (1-mix) gy + (corr)[:n]; mono input receives the sum of both channel rows
-__global__ void finish_dx_kernel(const float* __restrict__ gy, const float* __restrict__ apad,
-                                 const float* __restrict__ params, float* __restrict__ gx, int64_t item0, int64_t items,
-                                 int64_t n, int64_t n2, int in_chs) {
-  const int64_t total = items * in_chs * n;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row_in = i / n, t = i - row_in * n;
-    const int64_t bl = row_in / in_chs;
-    const int c = (int)(row_in - bl * in_chs);
-    const int64_t b = item0 + bl;
-    const float mix = params[b * 25 + 24];
-    float v;
-    if (in_chs == 1) {
-      const float g0 = gy[(b * 2 + 0) * n + t], g1 = gy[(b * 2 + 1) * n + t];
-      v = (1.0f - mix) * (g0 + g1) + apad[(bl * 2 + 0) * n2 + t] + apad[(bl * 2 + 1) * n2 + t];
-    } else {
-      v = fmaf(1.0f - mix, gy[(b * 2 + c) * n + t], apad[(bl * 2 + c) * n2 + t]);
-    }
-    gx[(b * in_chs + c) * n + t] = v;
+// gx[t] = (1-mix) g[t] + Dt[q][t - (q-1) kB] + Dt[q+1][t - q kB], q = t / kB (every sample sits in two windows);
+// mono input receives the sum of both channel gradients
+__global__ void finish_dx_blocks_kernel(const float* __restrict__ gy, const float2* __restrict__ Dt,
+                                        const float* __restrict__ params, float* __restrict__ gx, int64_t item0, int I,
+                                        int64_t n, int in_chs) {
+  const int i = blockIdx.x;
+  const int64_t il = blockIdx.y, b = item0 + il;
+  const float mix = params[b * 25 + 24];
+  const float2* d0 = Dt + (il * I + i) * (int64_t)kNbA + kB;
+  const float2* d1 = (i + 1 < I) ? Dt + (il * I + i + 1) * (int64_t)kNbA : nullptr;
+  for (int m = threadIdx.x; m < kB; m += blockDim.x) {
+    const int64_t t = (int64_t)i * kB + m;
+    if (t >= n) break;
+    float2 v = d0[m];
+    if (d1) { const float2 u = d1[m]; v.x += u.x; v.y += u.y; }
+    const float g0 = gy[(b * 2 + 0) * n + t], g1 = gy[(b * 2 + 1) * n + t];
+    const float o0 = fmaf(1.0f - mix, g0, v.x), o1 = fmaf(1.0f - mix, g1, v.y);
+    if (in_chs == 1) gx[b * n + t] = o0 + o1;
+    else { gx[(b * 2 + 0) * n + t] = o0; gx[(b * 2 + 1) * n + t] = o1; }
   }
 }
 
 // per (item, block): S0[k] = sum_t (dIR_l f_l + dIR_r f_r) env_k ;  S1[k] = sum_t (...) env_k tt
 // part[((item*nbk + b)*12 + k)*2 + {0,1}]
-__global__ void ir_grad_pairs_kernel(const float* __restrict__ dir_pad, const float2* __restrict__ C,
+__global__ void ir_grad_pairs_kernel(const float2* __restrict__ Et, const float2* __restrict__ C,
                                      const float* __restrict__ params, float* __restrict__ part, int64_t L,
-                                     int64_t leff, int64_t n2, int nbk, int nb, int hop, int P) {
+                                     int64_t leff, int jb, int nbk, int nb, int hop, int P) {
   const int b = blockIdx.x;
   const int64_t il = blockIdx.y;
   __shared__ float rk[kBands];
@@ -555,8 +634,7 @@ __global__ void ir_grad_pairs_kernel(const float* __restrict__ dir_pad, const fl
   if (threadIdx.x < kBands) rk[threadIdx.x] = -(params[il * 25 + kBands + threadIdx.x] * 10.0f + 1.0f);
   __syncthreads();
   const float step = 1.0f / (float)(L - 1);
-  const float* dl = dir_pad + (il * 2 + 0) * n2;
-  const float* dr = dir_pad + (il * 2 + 1) * n2;
+  const float2* de = Et + il * (int64_t)jb * kNbA;
   float s0[kBands], s1[kBands];
 #pragma unroll
   for (int k = 0; k < kBands; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
@@ -564,7 +642,8 @@ __global__ void ir_grad_pairs_kernel(const float* __restrict__ dir_pad, const fl
     const int64_t t = (int64_t)b * hop + m;
     if (t >= leff) break;
     const float tt = time_axis(t, L, step);
-    const float gl = dl[t], gr = dr[t];
+    const float2 gd = de[(t / kB) * kNbA + (t % kB)];
+    const float gl = gd.x, gr = gd.y;
     const float2* c = C + ((il * kBands) * nbk + b) * (int64_t)nb + m + P;
 #pragma unroll
     for (int k = 0; k < kBands; ++k) {
@@ -605,8 +684,7 @@ __global__ void reverb_param_grad_kernel(const float* __restrict__ ir_part, cons
     if (q < kBands) s *= (1.0 / kBands);
     else s *= (double)pp[k] * (-10.0 / kBands);
   } else {
-    for (int c = 0; c < 2; ++c)
-      for (int i = 0; i < mix_blocks; ++i) s += (double)mix_part[(bl * 2 + c) * mix_blocks + i];
+    for (int i = 0; i < mix_blocks; ++i) s += (double)mix_part[bl * mix_blocks + i];
   }
   gparams[(item0 + bl) * 25 + q] = (float)s;
 }
@@ -707,52 +785,57 @@ bool dispatch_spectral(int R, float2* C, const float2* H1, int64_t item0, int64_
 }
 constexpr int kMaxSpectralR = 16;
 
-struct Plans { PlanVal blk_c2c, pp_c2c, big_r2c, big_c2r; size_t work; };
+struct Plans { PlanVal blk_c2c, pp_c2c, xi_c2c, hj_c2c; size_t work; };
 int get_plans(const Geom& g, int64_t items, Plans& p) {
   int rc;
-  const int64_t nblocks = items * kBands * g.nbk;
-  if ((rc = get_plan(2, g.nb, nblocks, g.nb, g.nb, p.blk_c2c)) != DASP_OK) return rc;
+  if ((rc = get_plan(2, g.nb, items * kBands * g.nbk, g.nb, g.nb, p.blk_c2c)) != DASP_OK) return rc;
   if ((rc = get_plan(2, g.nb, items * kBands * g.rpp, g.nb, g.nb, p.pp_c2c)) != DASP_OK) return rc;
-  if ((rc = get_plan(0, g.n2, items * 2, g.n2, g.n2c(), p.big_r2c)) != DASP_OK) return rc;
-  if ((rc = get_plan(1, g.n2, items * 2, g.n2c(), g.n2, p.big_c2r)) != DASP_OK) return rc;
+  if ((rc = get_plan(2, kNbA, items * g.ib, kNbA, kNbA, p.xi_c2c)) != DASP_OK) return rc;
+  if ((rc = get_plan(2, kNbA, items * g.jb, kNbA, kNbA, p.hj_c2c)) != DASP_OK) return rc;
   p.work = p.blk_c2c.work;
   if (p.pp_c2c.work > p.work) p.work = p.pp_c2c.work;
-  if (p.big_r2c.work > p.work) p.work = p.big_r2c.work;
-  if (p.big_c2r.work > p.work) p.work = p.big_c2r.work;
+  if (p.xi_c2c.work > p.work) p.work = p.xi_c2c.work;
+  if (p.hj_c2c.work > p.work) p.work = p.hj_c2c.work;
   return DASP_OK;
 }
 
 inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // workspace carve-up shared by the geometry query and the two entry points
-struct FwdWs { size_t irpad, xpad, yspec, xsp, isp, fchunk, cufft, total; };
-struct BwdWs { size_t gpad, bpad, gspec, aspec, bspec, irpart, mixpart, cufft, total; };
-constexpr int kMixBlocks = 32;
+struct FwdWs { size_t ys, xsp, hsp, fchunk, cufft, total; };
+struct BwdWs { size_t gs, ds, es, irpart, mixpart, cufft, total; };
 
 void fwd_layout(const Geom& g, size_t cufft_work, FwdWs& w) {
   size_t o = 0;
-  w.irpad = o; o += align256(sizeof(float) * (size_t)(g.chunk * 2 * g.n2));
-  w.xpad = o;  o += align256(sizeof(float) * (size_t)(g.chunk * 2 * g.n2));
-  w.yspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
+  w.ys = o;  o += align256(sizeof(float2) * (size_t)(g.chunk * g.ib * kNbA));
   // transient homes for what a forward WITHOUT a backward does not keep (null *_save pointers)
-  w.xsp = o;   o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
-  w.isp = o;   o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
+  w.xsp = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.ib * kNbA));
+  w.hsp = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.jb * kNbA));
   w.fchunk = o; o += align256(sizeof(float2) * (size_t)(g.chunk * kBands * g.pair_c64()));
   w.cufft = o; o += align256(cufft_work);
   w.total = o;
 }
 void bwd_layout(const Geom& g, size_t cufft_work, BwdWs& w) {
   size_t o = 0;
-  w.gpad = o;  o += align256(sizeof(float) * (size_t)(g.chunk * 2 * g.n2));
-  w.bpad = o;  o += align256(sizeof(float) * (size_t)(g.chunk * 2 * g.n2));
-  w.gspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
-  w.aspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
-  w.bspec = o; o += align256(sizeof(cufftComplex) * (size_t)(g.chunk * 2 * g.n2c()));
+  w.gs = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.ib * kNbA));
+  w.ds = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.ib * kNbA));
+  w.es = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.jb * kNbA));
   const int64_t nparts = g.nbk > g.nparts_pp() ? g.nbk : g.nparts_pp();
   w.irpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * nparts * kBands * 2));
-  w.mixpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * 2 * kMixBlocks));
+  w.mixpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * g.ib));
   w.cufft = o; o += align256(cufft_work);
   w.total = o;
+}
+
+// out = conv / corr of packed block spectra, register-cached when both operands have <= 16 blocks
+template <bool CORR>
+void launch_mac(const float2* A, const float2* Bm, float2* Out, int na, int nbm, int nout, int64_t items, float scale,
+                cudaStream_t st) {
+  dim3 grid((kNbA / 2 + 1 + 127) / 128, (unsigned)items);
+  const int m = na > nbm ? na : nbm;
+  if (m <= 12)      partition_mac_kernel<12, CORR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
+  else if (m <= 16) partition_mac_kernel<16, CORR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
+  else              partition_mac_kernel<0, CORR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
 }
 
 }  // namespace
@@ -810,9 +893,11 @@ int dasp_reverb_geometry(int64_t bs, int64_t n, int64_t num_samples, int64_t tap
   FwdWs fw; BwdWs bw;
   fwd_layout(g, work, fw);
   bwd_layout(g, work, bw);
-  out->nb = g.nb; out->hop = g.hop; out->nbk = g.nbk; out->leff = g.leff; out->n2 = g.n2; out->chunk_items = g.chunk;
+  out->nb = g.nb; out->hop = g.hop; out->nbk = g.nbk; out->leff = g.leff; out->rpp = g.rpp;
+  out->conv_block = kB; out->x_blocks = g.ib; out->ir_partitions = g.jb; out->chunk_items = g.chunk;
   out->f_floats = bs * kBands * g.pair_c64() * 2;
-  out->spec_c64 = bs * 2 * g.n2c();
+  out->xspec_c64 = bs * g.ib * kNbA;
+  out->irspec_c64 = bs * g.jb * kNbA;
   out->wet_floats = bs * 2 * n;
   out->fwd_workspace_bytes = (int64_t)fw.total;
   out->bwd_workspace_bytes = (int64_t)bw.total;
@@ -845,35 +930,32 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     return DASP_ERR_WORKSPACE;
   }
   unsigned char* base = (unsigned char*)workspace;
-  float* ws_irpad = (float*)(base + w.irpad);
-  float* ws_xpad = (float*)(base + w.xpad);
-  cufftComplex* ws_yspec = (cufftComplex*)(base + w.yspec);
+  float2* ws_ys = (float2*)(base + w.ys);
   void* ws_cufft = base + w.cufft;
   const int64_t lp = g.L + g.P;
-  const int nbk = (int)g.nbk, nb = (int)g.nb, hop = (int)g.hop, P = (int)g.P;
+  const int nbk = (int)g.nbk, nb = (int)g.nb, hop = (int)g.hop, P = (int)g.P, I = (int)g.ib, J = (int)g.jb;
 
   for (int64_t item0 = 0; item0 < bs; item0 += g.chunk) {
     const int64_t items = (bs - item0 < g.chunk) ? bs - item0 : g.chunk;
     const Plans& pl = (items == g.chunk) ? pfull : prem;
-    const int64_t rows = items * 2;
     // kept for the backward when the caller passes *_save buffers, transient workspace otherwise
     float2* C = f_save ? reinterpret_cast<float2*>(f_save) + item0 * kBands * g.pair_c64()
                        : reinterpret_cast<float2*>(base + w.fchunk);
-    cufftComplex* xs = xspec_save ? (cufftComplex*)xspec_save + item0 * 2 * g.n2c() : (cufftComplex*)(base + w.xsp);
-    cufftComplex* is = irspec_save ? (cufftComplex*)irspec_save + item0 * 2 * g.n2c() : (cufftComplex*)(base + w.isp);
+    float2* xs = xspec_save ? (float2*)xspec_save + item0 * I * (int64_t)kNbA : (float2*)(base + w.xsp);
+    float2* hs = irspec_save ? (float2*)irspec_save + item0 * J * (int64_t)kNbA : (float2*)(base + w.hsp);
     const dim3 gblk((unsigned)nbk, kBands, (unsigned)items);
 
-    // ---- IR synthesis ----
-    if (!noise && g.rpp <= kMaxSpectralR) {
+    // ---- IR synthesis: (left, right) taps land in the zero-initialised partition layout hs ----
+    DASP_CUDA_OK(cudaMemsetAsync(hs, 0, sizeof(float2) * items * J * kNbA, st));
+    if (spectral) {
       // device noise: draw the filtered spectrum directly, one inverse transform (polyphase layout)
       dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, (unsigned long long)seed, st);
       DASP_LAUNCH_OK("spectral_gen_kernel");
       DASP_CUFFT_OK(cufftSetStream(pl.pp_c2c.h, st));
       DASP_CUFFT_OK(cufftSetWorkArea(pl.pp_c2c.h, ws_cufft));
       DASP_CUFFT_OK(cufftExecC2C(pl.pp_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_INVERSE));
-      DASP_CUDA_OK(cudaMemsetAsync(ws_irpad, 0, sizeof(float) * rows * g.n2, st));
       shape_ir_pp_kernel<<<dim3((unsigned)g.nparts_pp(), (unsigned)items), 256, 0, st>>>(
-          C, params + item0 * 25, ws_irpad, g.L, g.leff, g.n2, (int)g.rpp, nb);
+          C, params + item0 * 25, hs, g.L, g.leff, J, (int)g.rpp, nb);
       DASP_LAUNCH_OK("shape_ir_pp_kernel");
     } else {
       // parity mode (caller's noise tensor) or very long IR: time-domain noise, overlap-save blocks
@@ -886,25 +968,26 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
       cmul_filter_pairs_kernel<<<gblk, 256, 0, st>>>(C, H, nbk, nb);
       DASP_LAUNCH_OK("cmul_filter_pairs_kernel");
       DASP_CUFFT_OK(cufftExecC2C(pl.blk_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_INVERSE));
-      shape_ir_pairs_kernel<<<dim3((unsigned)((g.n2 + hop - 1) / hop), (unsigned)items), 256, 0, st>>>(
-          C, params + item0 * 25, ws_irpad, g.L, g.leff, g.n2, nbk, nb, hop, P);
+      shape_ir_pairs_kernel<<<dim3((unsigned)nbk, (unsigned)items), 256, 0, st>>>(C, params + item0 * 25, hs, g.L, g.leff,
+                                                                               J, nbk, nb, hop, P);
       DASP_LAUNCH_OK("shape_ir_pairs_kernel");
     }
 
-    // ---- apply ----
-    pad_x_kernel<<<grid_for(rows * g.n2), 256, 0, st>>>(x, ws_xpad, item0, rows, n, g.n2, (int)in_chs);
-    DASP_LAUNCH_OK("pad_x_kernel");
-    DASP_CUFFT_OK(cufftSetStream(pl.big_r2c.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.big_r2c.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecR2C(pl.big_r2c.h, ws_irpad, is));
-    DASP_CUFFT_OK(cufftExecR2C(pl.big_r2c.h, ws_xpad, xs));
-    cmul_kernel<false><<<grid_for(rows * g.n2c()), 256, 0, st>>>(xs, is, ws_yspec, rows * g.n2c(), 1.0f / (float)g.n2);
-    DASP_LAUNCH_OK("cmul_kernel");
-    DASP_CUFFT_OK(cufftSetStream(pl.big_c2r.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.big_c2r.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecC2R(pl.big_c2r.h, ws_yspec, ws_irpad));      // irpad is free again: reuse as ypad
-    mix_kernel<<<grid_for(rows * n), 256, 0, st>>>(x, ws_irpad, params, y, wet_save, item0, rows, n, g.n2, (int)in_chs);
-    DASP_LAUNCH_OK("mix_kernel");
+    // ---- audio convolution (partitioned, frequency domain) ----
+    x_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(x, xs, item0, I, n, (int)in_chs);
+    DASP_LAUNCH_OK("x_blocks_kernel");
+    DASP_CUFFT_OK(cufftSetStream(pl.hj_c2c.h, st));
+    DASP_CUFFT_OK(cufftSetWorkArea(pl.hj_c2c.h, ws_cufft));
+    DASP_CUFFT_OK(cufftExecC2C(pl.hj_c2c.h, (cufftComplex*)hs, (cufftComplex*)hs, CUFFT_FORWARD));
+    DASP_CUFFT_OK(cufftSetStream(pl.xi_c2c.h, st));
+    DASP_CUFFT_OK(cufftSetWorkArea(pl.xi_c2c.h, ws_cufft));
+    DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)xs, (cufftComplex*)xs, CUFFT_FORWARD));
+    launch_mac<false>(xs, hs, ws_ys, I, J, I, items, 1.0f / (float)kNbA, st);
+    DASP_LAUNCH_OK("partition_mac_kernel");
+    DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)ws_ys, (cufftComplex*)ws_ys, CUFFT_INVERSE));
+    mix_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(x, ws_ys, params, y, wet_save, item0, I, n,
+                                                                        (int)in_chs);
+    DASP_LAUNCH_OK("mix_blocks_kernel");
   }
   return DASP_OK;
 }
@@ -933,54 +1016,51 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
     return DASP_ERR_WORKSPACE;
   }
   unsigned char* base = (unsigned char*)workspace;
-  float* ws_gpad = (float*)(base + w.gpad);
-  float* ws_bpad = (float*)(base + w.bpad);
-  cufftComplex* ws_gspec = (cufftComplex*)(base + w.gspec);
-  cufftComplex* ws_aspec = (cufftComplex*)(base + w.aspec);
-  cufftComplex* ws_bspec = (cufftComplex*)(base + w.bspec);
+  float2* ws_gs = (float2*)(base + w.gs);
+  float2* ws_ds = (float2*)(base + w.ds);
+  float2* ws_es = (float2*)(base + w.es);
   float* ws_irpart = (float*)(base + w.irpart);
   float* ws_mixpart = (float*)(base + w.mixpart);
   void* ws_cufft = base + w.cufft;
-  const float inv_n2 = 1.0f / (float)g.n2;
-  const int nbk = (int)g.nbk, nb = (int)g.nb, hop = (int)g.hop, P = (int)g.P;
+  const float inv = 1.0f / (float)kNbA;
+  const int nbk = (int)g.nbk, nb = (int)g.nb, hop = (int)g.hop, P = (int)g.P, I = (int)g.ib, J = (int)g.jb;
 
   for (int64_t item0 = 0; item0 < bs; item0 += g.chunk) {
     const int64_t items = (bs - item0 < g.chunk) ? bs - item0 : g.chunk;
     const Plans& pl = (items == g.chunk) ? pfull : prem;
-    const int64_t rows = items * 2;
     const float2* C = reinterpret_cast<const float2*>(f_save) + item0 * kBands * g.pair_c64();
-    const cufftComplex* xs = (const cufftComplex*)xspec_save + item0 * 2 * g.n2c();
-    const cufftComplex* is = (const cufftComplex*)irspec_save + item0 * 2 * g.n2c();
+    const float2* xs = (const float2*)xspec_save + item0 * I * (int64_t)kNbA;
+    const float2* hs = (const float2*)irspec_save + item0 * J * (int64_t)kNbA;
 
-    pad_g_kernel<<<dim3(kMixBlocks, (unsigned)rows), 256, 0, st>>>(gy, x, wet_save, params, ws_gpad, ws_mixpart, item0, n,
-                                                                   g.n2, (int)in_chs);
-    DASP_LAUNCH_OK("pad_g_kernel");
-    DASP_CUFFT_OK(cufftSetStream(pl.big_r2c.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.big_r2c.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecR2C(pl.big_r2c.h, ws_gpad, ws_gspec));
-    cmul_kernel<true><<<grid_for(rows * g.n2c()), 256, 0, st>>>(ws_gspec, is, ws_aspec, rows * g.n2c(), inv_n2);
-    cmul_kernel<true><<<grid_for(rows * g.n2c()), 256, 0, st>>>(ws_gspec, xs, ws_bspec, rows * g.n2c(), inv_n2);
-    DASP_LAUNCH_OK("cmul_kernel<conj>");
-    DASP_CUFFT_OK(cufftSetStream(pl.big_c2r.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.big_c2r.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecC2R(pl.big_c2r.h, ws_aspec, ws_gpad));       // gpad reused: dL/dx correlation term
-    DASP_CUFFT_OK(cufftExecC2R(pl.big_c2r.h, ws_bspec, ws_bpad));       // dL/dIR (first leff samples)
-    finish_dx_kernel<<<grid_for(items * in_chs * n), 256, 0, st>>>(gy, ws_gpad, params, gx, item0, items, n, g.n2,
-                                                                   (int)in_chs);
-    DASP_LAUNCH_OK("finish_dx_kernel");
+    g_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(gy, x, wet_save, params, ws_gs, ws_mixpart, item0, I,
+                                                                      n, (int)in_chs);
+    DASP_LAUNCH_OK("g_blocks_kernel");
+    DASP_CUFFT_OK(cufftSetStream(pl.xi_c2c.h, st));
+    DASP_CUFFT_OK(cufftSetWorkArea(pl.xi_c2c.h, ws_cufft));
+    DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)ws_gs, (cufftComplex*)ws_gs, CUFFT_FORWARD));
+    launch_mac<true>(ws_gs, hs, ws_ds, I, J, I, items, inv, st);      // dx windows: sum_j conj(H[j]) G[q+j]
+    launch_mac<true>(ws_gs, xs, ws_es, I, I, J, items, inv, st);      // dIR partitions: sum_p conj(X[p]) G[j+p]
+    DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+    DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)ws_ds, (cufftComplex*)ws_ds, CUFFT_INVERSE));
+    DASP_CUFFT_OK(cufftSetStream(pl.hj_c2c.h, st));
+    DASP_CUFFT_OK(cufftSetWorkArea(pl.hj_c2c.h, ws_cufft));
+    DASP_CUFFT_OK(cufftExecC2C(pl.hj_c2c.h, (cufftComplex*)ws_es, (cufftComplex*)ws_es, CUFFT_INVERSE));
+    finish_dx_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(gy, ws_ds, params, gx, item0, I, n,
+                                                                              (int)in_chs);
+    DASP_LAUNCH_OK("finish_dx_blocks_kernel");
     int nparts;
     if (polyphase) {
       nparts = (int)g.nparts_pp();
-      ir_grad_pp_kernel<<<dim3((unsigned)nparts, (unsigned)items), 256, 0, st>>>(ws_bpad, C, params + item0 * 25, ws_irpart,
-                                                                                g.L, g.leff, g.n2, (int)g.rpp, nb);
+      ir_grad_pp_kernel<<<dim3((unsigned)nparts, (unsigned)items), 256, 0, st>>>(ws_es, C, params + item0 * 25, ws_irpart,
+                                                                                g.L, g.leff, J, (int)g.rpp, nb);
     } else {
       nparts = nbk;
-      ir_grad_pairs_kernel<<<dim3((unsigned)nbk, (unsigned)items), 256, 0, st>>>(ws_bpad, C, params + item0 * 25, ws_irpart,
-                                                                                  g.L, g.leff, g.n2, nbk, nb, hop, P);
+      ir_grad_pairs_kernel<<<dim3((unsigned)nbk, (unsigned)items), 256, 0, st>>>(ws_es, C, params + item0 * 25, ws_irpart,
+                                                                                  g.L, g.leff, J, nbk, nb, hop, P);
     }
     DASP_LAUNCH_OK("ir_grad kernel");
     reverb_param_grad_kernel<<<(unsigned)((items * 25 + 127) / 128), 128, 0, st>>>(ws_irpart, ws_mixpart, params, gparams,
-                                                                                   item0, items, nparts, kMixBlocks);
+                                                                                   item0, items, nparts, I);
     DASP_LAUNCH_OK("reverb_param_grad_kernel");
   }
   return DASP_OK;

@@ -410,8 +410,8 @@ class _ReverbFn(torch.autograd.Function):
             if need_bwd:
                 wet = torch.empty(geom.wet_floats, dtype=torch.float32, device=dev)
                 fsave = torch.empty(geom.f_floats, dtype=torch.float32, device=dev)
-                xspec = torch.empty(geom.spec_c64, dtype=torch.complex64, device=dev)
-                irspec = torch.empty(geom.spec_c64, dtype=torch.complex64, device=dev)
+                xspec = torch.empty(geom.xspec_c64, dtype=torch.complex64, device=dev)
+                irspec = torch.empty(geom.irspec_c64, dtype=torch.complex64, device=dev)
             with _timed("reverb_fwd", dev):
                 check(lib.dasp_reverb_fwd(ptr(x), in_chs, ptr(params), ptr(noise), int(seed), ptr(y), ptr(wet),
                                           ptr(fsave), ptr(xspec), ptr(irspec), ptr(ws), ws.numel(), bs, n, num_samples,

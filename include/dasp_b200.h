@@ -102,14 +102,17 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
  * Buffers kept for the backward (pass NULL for all four when no backward follows):
  *   wet_save  bs*2*n floats, f_save  geom.f_floats floats (band-filtered noise blocks, left/right
  *   channel interleaved as complex pairs),
- *   xspec_save / irspec_save  geom.spec_c64 complex64 each.
+ *   xspec_save  geom.xspec_c64 complex64, irspec_save  geom.irspec_c64 complex64 (block spectra).
  * workspace: geom.fwd_workspace_bytes / geom.bwd_workspace_bytes bytes of device memory. */
 typedef struct dasp_reverb_geom {
-  int64_t nb, hop, nbk;       /* overlap-save block length, hop and blocks per band signal */
+  int64_t nb, hop, nbk;       /* IR synthesis, overlap-save path: block length, hop, blocks per band signal */
   int64_t leff;               /* min(num_samples, n): IR taps that can reach the n output samples */
-  int64_t n2;                 /* FFT length of the audio convolution (>= n + leff - 1, 7-smooth) */
-  int64_t chunk_items;        /* items processed per pass (L2-sized working set) */
-  int64_t f_floats, spec_c64, wet_floats;
+  int64_t rpp;                /* IR synthesis, spectral path: polyphase factor (n1 = rpp * nb >= leff + taps - 1) */
+  int64_t conv_block;         /* audio convolution: partition / hop length (its FFT length is twice that) */
+  int64_t x_blocks;           /* ceil(n / conv_block) */
+  int64_t ir_partitions;      /* ceil(leff / conv_block) */
+  int64_t chunk_items;        /* items processed per pass */
+  int64_t f_floats, xspec_c64, irspec_c64, wet_floats;      /* sizes of the buffers kept for the backward */
   int64_t fwd_workspace_bytes, bwd_workspace_bytes;
 } dasp_reverb_geom;
 int dasp_reverb_geometry(int64_t bs, int64_t n, int64_t num_samples, int64_t taps, int64_t chunk_items,
