@@ -259,6 +259,29 @@ __global__ void cmul_filter_pairs_kernel(float2* __restrict__ C, const float2* _
 //   Q_b[j1] = e^{2 pi i j1 b / n1} * sum_{j2<R} G[j1 + nb j2] e^{2 pi i j2 b / R}
 // Polyphase layout: C[((item*12 + k)*R + b)*nb + a] = (f_left, f_right)[R a + b].
 // Left/right are packed as G_left + i G_right; one Philox call per canonical bin yields both channels.
+// Philox4x32-10 (Salmon et al., SC'11), counter = (c0, c1, c2, c3), key = (k0, k1); written out instead of the
+// cuRAND state machinery because this kernel needs exactly one block of 4 words per call site
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c.x;
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c.z;
+    c = make_uint4((unsigned)(p1 >> 32) ^ c.y ^ k.x, (unsigned)p1, (unsigned)(p0 >> 32) ^ c.w ^ k.y, (unsigned)p0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+// two independent N(0,1) from two 32-bit words (Box-Muller; u1 in (0,1], angle in turns)
+__device__ __forceinline__ float2 box_muller(unsigned a, unsigned b) {
+  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;       // (a+1) / 2^32, rounds into (0, 1]
+  const float u2 = (float)b * 2.3283064365386963e-10f;
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  sincospif(2.0f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+
 template <int R>
 __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __restrict__ H1, int64_t item0, int nb,
                                     unsigned long long seed) {
@@ -274,12 +297,13 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
   // value of the packed spectrum G_left + i G_right at bin j (0 <= j < n1) and at its mirror n1 - j
   auto draw = [&](int j, float2& at_j, float2& at_mirror) {
     const int jc = j <= n1h ? j : n1 - j;
-    curandStatePhilox4_32_10_t st;
-    curand_init(seed, (pair << 24) + (unsigned long long)jc, 0ull, &st);
-    const float4 z = curand_normal4(&st);
+    // counter = (canonical bin, band pair), key = seed: one Philox block -> both channels' complex Gaussian
+    const uint4 rnd = philox4x32_10(make_uint4((unsigned)jc, (unsigned)pair, (unsigned)(pair >> 32), 0x5eedu),
+                                    make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const float2 nl = box_muller(rnd.x, rnd.y), nr = box_muller(rnd.z, rnd.w);
     float2 zl, zr;
-    if (jc == 0 || jc == n1h) { zl = make_float2(z.x * s_full, 0.f); zr = make_float2(z.z * s_full, 0.f); }
-    else { zl = make_float2(z.x * s_half, z.y * s_half); zr = make_float2(z.z * s_half, z.w * s_half); }
+    if (jc == 0 || jc == n1h) { zl = make_float2(nl.x * s_full, 0.f); zr = make_float2(nr.x * s_full, 0.f); }
+    else { zl = make_float2(nl.x * s_half, nl.y * s_half); zr = make_float2(nr.x * s_half, nr.y * s_half); }
     const float2 w = h[jc];
     const float2 sl = make_float2(w.x * zl.x - w.y * zl.y, w.x * zl.y + w.y * zl.x);   // H Z_left
     const float2 sr = make_float2(w.x * zr.x - w.y * zr.y, w.x * zr.y + w.y * zr.x);   // H Z_right
@@ -363,10 +387,11 @@ __global__ void shape_ir_pairs_kernel(const float2* __restrict__ C, const float*
   }
 }
 
-// polyphase layout variant: thread a handles times R a .. R a + R - 1 (irpad tail is pre-zeroed by memset)
+// polyphase layout variant, threads in TIME order (coalesced IR stores; the 12 band loads of a thread are
+// issued together).  grid = (ceil(leff / 256), items)
 __global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __restrict__ params, float2* __restrict__ Hb,
                                    int64_t L, int64_t leff, int jb, int R, int nb) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t il = blockIdx.y;
   __shared__ float gk[kBands], rk[kBands];
   if (threadIdx.x < kBands) {
@@ -374,31 +399,27 @@ __global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __
     rk[threadIdx.x] = -(params[il * 25 + kBands + threadIdx.x] * 10.0f + 1.0f);
   }
   __syncthreads();
-  if (a >= nb) return;
-  const float step = 1.0f / (float)(L - 1);
-  float2* out = Hb + il * (int64_t)jb * kNbA;
-  const float2* c0 = C + (il * kBands) * (int64_t)R * nb + a;
-  for (int ph = 0; ph < R; ++ph) {
-    const int64_t t = (int64_t)R * a + ph;
-    if (t >= leff) break;
-    const float tt = time_axis(t, L, step);
-    float al = 0.f, ar = 0.f;
+  if (t >= leff) return;
+  const int a = t / R, ph = t - a * R;
+  const float tt = time_axis(t, L, 1.0f / (float)(L - 1));
+  const float2* c0 = C + ((il * kBands) * (int64_t)R + ph) * nb + a;
+  float2 v[kBands];
 #pragma unroll
-    for (int k = 0; k < kBands; ++k) {
-      const float2 v = c0[((int64_t)k * R + ph) * nb];
-      const float e = gk[k] * expf(rk[k] * tt);
-      al = fmaf(e, v.x, al);
-      ar = fmaf(e, v.y, ar);
-    }
-    out[(t / kB) * kNbA + (t % kB)] = make_float2(al, ar);
+  for (int k = 0; k < kBands; ++k) v[k] = c0[(int64_t)k * R * nb];
+  float al = 0.f, ar = 0.f;
+#pragma unroll
+  for (int k = 0; k < kBands; ++k) {
+    const float e = gk[k] * __expf(rk[k] * tt);
+    al = fmaf(e, v[k].x, al);
+    ar = fmaf(e, v[k].y, ar);
   }
+  Hb[il * (int64_t)jb * kNbA + (t / kB) * kNbA + (t % kB)] = make_float2(al, ar);
 }
 
-// part[((item*nparts + blockIdx.x)*12 + k)*2 + {0,1}], nparts = gridDim.x
+// part[((item*nparts + blockIdx.x)*12 + k)*2 + {0,1}], nparts = gridDim.x; threads stride over time
 __global__ void ir_grad_pp_kernel(const float2* __restrict__ Et, const float2* __restrict__ C,
                                   const float* __restrict__ params, float* __restrict__ part, int64_t L, int64_t leff,
                                   int jb, int R, int nb) {
-  const int a = blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t il = blockIdx.y;
   __shared__ float rk[kBands];
   __shared__ float red[8][2 * kBands];
@@ -406,24 +427,23 @@ __global__ void ir_grad_pp_kernel(const float2* __restrict__ Et, const float2* _
   __syncthreads();
   const float step = 1.0f / (float)(L - 1);
   const float2* de = Et + il * (int64_t)jb * kNbA;       // dL/dIR (left, right) in the first half of partition t/kB
+  const float2* cb = C + (il * kBands) * (int64_t)R * nb;
   float s0[kBands], s1[kBands];
 #pragma unroll
   for (int k = 0; k < kBands; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
-  if (a < nb) {
-    const float2* c0 = C + (il * kBands) * (int64_t)R * nb + a;
-    for (int ph = 0; ph < R; ++ph) {
-      const int64_t t = (int64_t)R * a + ph;
-      if (t >= leff) break;
-      const float tt = time_axis(t, L, step);
-      const float2 gd = de[(t / kB) * kNbA + (t % kB)];
-      const float gl = gd.x, gr = gd.y;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < leff; t += gridDim.x * blockDim.x) {
+    const int a = t / R, ph = t - a * R;
+    const float2 gd = de[(t / kB) * kNbA + (t % kB)];
+    const float2* c0 = cb + (int64_t)ph * nb + a;
+    float2 v[kBands];
 #pragma unroll
-      for (int k = 0; k < kBands; ++k) {
-        const float2 v = c0[((int64_t)k * R + ph) * nb];
-        const float w = fmaf(gl, v.x, gr * v.y) * expf(rk[k] * tt);
-        s0[k] += w;
-        s1[k] = fmaf(w, tt, s1[k]);
-      }
+    for (int k = 0; k < kBands; ++k) v[k] = c0[(int64_t)k * R * nb];
+    const float tt = time_axis(t, L, step);
+#pragma unroll
+    for (int k = 0; k < kBands; ++k) {
+      const float w = fmaf(gd.x, v[k].x, gd.y * v[k].y) * __expf(rk[k] * tt);
+      s0[k] += w;
+      s1[k] = fmaf(w, tt, s1[k]);
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -954,7 +974,7 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
       DASP_CUFFT_OK(cufftSetStream(pl.pp_c2c.h, st));
       DASP_CUFFT_OK(cufftSetWorkArea(pl.pp_c2c.h, ws_cufft));
       DASP_CUFFT_OK(cufftExecC2C(pl.pp_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_INVERSE));
-      shape_ir_pp_kernel<<<dim3((unsigned)g.nparts_pp(), (unsigned)items), 256, 0, st>>>(
+      shape_ir_pp_kernel<<<dim3((unsigned)((g.leff + 255) / 256), (unsigned)items), 256, 0, st>>>(
           C, params + item0 * 25, hs, g.L, g.leff, J, (int)g.rpp, nb);
       DASP_LAUNCH_OK("shape_ir_pp_kernel");
     } else {

@@ -388,8 +388,8 @@ def parametric_eq(
 import os as _os
 
 # items per pass of the reverb pipeline (bounds the workspace; measured on B200: 8 -> 55 ms, 16 -> 42 ms,
-# 32 -> 34 ms per chain step at batch 1024; override for experiments with DASP_REVERB_CHUNK)
-REVERB_CHUNK_ITEMS = int(_os.environ.get("DASP_REVERB_CHUNK", "32"))
+# 32 -> 34 ms per chain step at batch 1024 (first pipeline); 128 is the default since the partitioned rewrite; override for experiments with DASP_REVERB_CHUNK)
+REVERB_CHUNK_ITEMS = int(_os.environ.get("DASP_REVERB_CHUNK", "128"))
 
 
 class _ReverbFn(torch.autograd.Function):
