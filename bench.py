@@ -235,13 +235,17 @@ def main():
     d_pin = drive_h.pin_memory()
 
     def to_leaves(xd, pd, dd):
+        # ONE leaf per tensor kind: the 49 per-item parameters stay packed as (bs, 49); the processors get
+        # column views, so the parameter gradients arrive packed as well (pd.grad)
         xd.requires_grad_(True)
-        cols = [pd[:, i].clone().requires_grad_(True) for i in range(49)]
+        pd.requires_grad_(True)
         dd.requires_grad_(True)
+        cols = list(pd.unbind(1))
         return xd, cols[:18], cols[18:24], cols[24:49], dd
 
     x, eq, comp, rev, drive = to_leaves(x_pin.to(dev), p_pin.to(dev), d_pin.to(dev))
-    leaves = [x] + eq + comp + rev + [drive]
+    p_dev = eq[0]._base if eq[0]._base is not None else None
+    leaves = [x, drive] + ([p_dev] if p_dev is not None else eq + comp + rev)
 
     def step():
         for t in leaves:
@@ -294,8 +298,7 @@ def main():
         y = chain(D, xx, e_, c_, r_, d_)
         loss = y.pow(2).mean()
         loss.backward()
-        grads = torch.stack([q.grad for q in e_ + c_[:3] + c_[4:] + r_], 1)
-        return float(loss.item()), grads.cpu(), d_.grad.cpu()
+        return float(loss.item()), pd.grad.cpu(), d_.grad.cpu()
 
     e2e_step()
     barrier()
@@ -309,7 +312,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * samples_per_step * args.steps / float(t.item())
     h2d = x_pin.numel() * 4 + p_pin.numel() * 4 + d_pin.numel() * 4
-    d2h = 4 + bs * 48 * 4 + bs * CHS * 4
+    d2h = 4 + bs * 49 * 4 + bs * CHS * 4
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
