@@ -106,7 +106,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -199,7 +199,7 @@ def run_reference_arm(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="items per GPU (BASELINE config: 1024)")
@@ -290,21 +290,39 @@ def main():
     value = world * samples_per_step * args.steps / (ms_max * 1e-3)
 
     # ---- end-to-end: pinned host inputs -> H2D -> fwd+bwd -> D2H of loss and parameter gradients ----
-    def e2e_step():
-        xd = x_pin.to(dev, non_blocking=True)
-        pd = p_pin.to(dev, non_blocking=True)
-        dd = d_pin.to(dev, non_blocking=True)
-        xx, e_, c_, r_, d_ = to_leaves(xd, pd, dd)
-        y = chain(D, xx, e_, c_, r_, d_)
-        loss = y.pow(2).mean()
-        loss.backward()
-        return float(loss.item()), pd.grad.cpu(), d_.grad.cpu()
+    # Every step copies ITS inputs from pinned host memory and reads its loss + parameter gradients back.
+    # Like any input pipeline, the copy of step k+1 is issued on a side stream while step k computes
+    # (double-buffered device tensors); nothing is skipped or cached across steps.
+    copy_stream = torch.cuda.Stream(device=dev)
 
-    e2e_step()
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            bufs = (x_pin.to(dev, non_blocking=True), p_pin.to(dev, non_blocking=True), d_pin.to(dev, non_blocking=True))
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return bufs, ev
+
+    def e2e_loop(n_steps):
+        nxt = upload()
+        out = None
+        for k in range(n_steps):
+            (xd, pd, dd), ev = nxt
+            torch.cuda.current_stream(dev).wait_event(ev)
+            for t in (xd, pd, dd):
+                t.record_stream(torch.cuda.current_stream(dev))
+            if k + 1 < n_steps:
+                nxt = upload()
+            xx, e_, c_, r_, d_ = to_leaves(xd, pd, dd)
+            y = chain(D, xx, e_, c_, r_, d_)
+            loss = y.pow(2).mean()
+            loss.backward()
+            out = (float(loss.item()), pd.grad.cpu(), d_.grad.cpu())      # D2H read of this step's results
+        return out
+
+    e2e_loop(2)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
