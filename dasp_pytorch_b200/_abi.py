@@ -12,7 +12,7 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdasp_b200.so")
+LIB_PATH = os.environ.get("DASP_LIB_PATH") or os.path.join(_HERE, "libdasp_b200.so")   # override: experiments only
 
 ABI_VERSION = 1
 

@@ -42,7 +42,13 @@
 namespace dasp {
 namespace {
 
-constexpr int kE = 15;           // samples per thread per tile (odd: conflict-free stride-E smem access)
+#ifndef DASP_EQ_E
+#define DASP_EQ_E 15
+#endif
+#ifndef DASP_EQ_WARPS_PER_SM
+#define DASP_EQ_WARPS_PER_SM 24
+#endif
+constexpr int kE = DASP_EQ_E;    // samples per thread per tile (odd: conflict-free stride-E smem access)
 constexpr int kStages = 3;
 constexpr int kSections = 6;
 constexpr int kNumPowTables = kE + 5 + 32 + 1;   // A^j (j<E) | A^(E 2^k) (k<5) | A^(E lane) | A^(32E)
@@ -529,7 +535,7 @@ __global__ void eq_param_grad_kernel(const float* __restrict__ partial, const fl
 
 // ---- host side -----------------------------------------------------------------------------
 int pick_warps(int64_t rows) {
-  const int64_t want = 12ll * sm_count();
+  const int64_t want = (int64_t)DASP_EQ_WARPS_PER_SM * sm_count();
   int w = 1;
   while (w < 4 && rows * w < want) w *= 2;
   return w;
