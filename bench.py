@@ -94,7 +94,9 @@ def chain(mod, x, eq, comp, rev, drive, **rev_kw):
 # ------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled in the background from before the warm-up; only the samples whose timestamps fall
+    inside the timed region [t0, t1] are reported."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -106,7 +108,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -117,29 +119,36 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
-    def stop(self):
+    def stop(self, t0, t1):
+        import datetime
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, sm_all, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             f = [c.strip() for c in r.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                clk, cmax = float(f[1]), float(f[2])
             except ValueError:
                 continue
+            sm_all.append(clk)
+            if not (t0 - 0.02 <= ts <= t1 + 0.02):
+                continue
+            sm.append(clk); mx.append(cmax)
             for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples_in_timed_region": len(sm), "samples_total": len(sm_all), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -260,23 +269,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
     barrier()
 
     # ---- timed region (device time, CUDA events on the launching stream) ----
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     F.STAGE_TIMING = []                       # per-stage CUDA events, see functional._timed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    wall0 = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     barrier()
+    wall1 = time.time()
     ms = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(wall0, wall1)
     stage_events = F.STAGE_TIMING
     F.STAGE_TIMING = None
     stages = {}
@@ -344,8 +355,10 @@ def main():
         }
         kern = {"eq_fwd": "eq_fwd_kernel", "eq_bwd": "eq_bwd_kernel", "comp_fwd": "dynamics_fwd_kernel",
                 "comp_bwd": "dynamics_bwd_kernel", "dist_fwd": "pointwise_fwd_kernel", "dist_bwd": "pointwise_bwd_kernel",
-                "reverb_fwd": "reverb fwd pipeline (cuFFT + noise/cmul_filter/shape_ir/cmul/mix kernels)",
-                "reverb_bwd": "reverb bwd pipeline (cuFFT + pad_g/cmul/finish_dx/ir_grad kernels)"}
+                "reverb_fwd": "reverb fwd pipeline: spectral_gen_kernel, cuFFT C2C(8192) x4, shape_ir_pp_kernel, "
+                              "x_blocks_kernel, partition_mac_kernel, mix_blocks_kernel",
+                "reverb_bwd": "reverb bwd pipeline: g_blocks_kernel, cuFFT C2C(8192) x3, partition_mac_kernel x2, "
+                              "finish_dx_blocks_kernel, ir_grad_pp_kernel"}
         breakdown = {}
         for name, v in stages.items():
             m = statistics.mean(v)

@@ -273,14 +273,18 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 // two independent N(0,1) from two 32-bit words (Box-Muller; u1 in (0,1], angle in turns)
+// MUFU-only transcendental path (lg2, rsq, sin, cos: |abs err| ~ 1e-6, irrelevant for a noise source) -- the
+// generator kernel is instruction-issue bound and the accurate logf/sqrtf/sincospif were ~55 % of it
 __device__ __forceinline__ float2 box_muller(unsigned a, unsigned b) {
   const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;       // (a+1) / 2^32, rounds into (0, 1]
-  const float u2 = (float)b * 2.3283064365386963e-10f;
-  const float r = sqrtf(-2.0f * __logf(u1));
-  float sn, cs;
-  sincospif(2.0f * u2, &sn, &cs);
-  return make_float2(r * cs, r * sn);
+  const float ang = ((float)b * 2.3283064365386963e-10f - 0.5f) * 6.283185307179586f;   // [-pi, pi)
+  const float m = -2.0f * __logf(u1);                                  // >= 0
+  const float r = m * rsqrtf(fmaxf(m, 1e-30f));                        // sqrt(m)
+  return make_float2(r * __cosf(ang), r * __sinf(ang));
 }
+
+// e^{2 pi i m / R} for every polyphase factor R <= 16 (filled once per device on the host side)
+__constant__ float2 c_root[17][16];
 
 template <int R>
 __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __restrict__ H1, int64_t item0, int nb,
@@ -323,7 +327,7 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
   }
   float2 root[R];
 #pragma unroll
-  for (int m = 0; m < R; ++m) sincospif(2.0f * (float)m / (float)R, &root[m].y, &root[m].x);
+  for (int m = 0; m < R; ++m) root[m] = c_root[R][m];
   float2 w1a, w1b;
   sincospif(2.0f * (float)j1 / (float)n1, &w1a.y, &w1a.x);
   sincospif(2.0f * (float)(nb - j1) / (float)n1, &w1b.y, &w1b.x);
@@ -759,6 +763,16 @@ int get_filterbank_n1(const Geom& g, double sr, cudaStream_t st, const float2** 
   auto it = g_fb.find(key);
   if (it != g_fb.end()) { *out = reinterpret_cast<const float2*>(it->second); return DASP_OK; }
   DASP_REQUIRE(sr / 2.0 > 18000.0, "sample_rate %.1f too low: the filter bank needs 18 kHz < sr/2 (signal.py:84)", sr);
+  {
+    float2 roots[17][16];
+    for (int r = 0; r <= 16; ++r)
+      for (int m = 0; m < 16; ++m) {
+        const double a = (r > 0) ? 2.0 * kPi * (double)(m % r) / (double)r : 0.0;
+        roots[r][m] = make_float2((float)cos(a), (float)sin(a));
+      }
+    DASP_CUDA_OK(cudaMemcpyToSymbolAsync(c_root, roots, sizeof(roots), 0, cudaMemcpyHostToDevice, st));
+    DASP_CUDA_OK(cudaStreamSynchronize(st));
+  }
   std::vector<float> taps;
   octave_filterbank((int)g.taps, sr, taps);
   std::vector<float> padded((size_t)kBands * n1, 0.f);
