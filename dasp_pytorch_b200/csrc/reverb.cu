@@ -169,28 +169,6 @@ struct FbKey {
 };
 
 std::mutex g_mu;
-// helper stream on which the (issue-bound) noise-spectrum generator of chunk k+1 runs while the
-// (bandwidth-bound) transforms of chunk k run on the caller's stream; ordered with events only
-struct AuxStream { cudaStream_t s = nullptr; cudaEvent_t entry = nullptr; cudaEvent_t gen_done[2] = {nullptr, nullptr};
-                   cudaEvent_t consumed[2] = {nullptr, nullptr}; };
-std::map<int, AuxStream> g_aux;
-int get_aux(AuxStream** out) {
-  int dev = 0;
-  DASP_CUDA_OK(cudaGetDevice(&dev));
-  AuxStream& a = g_aux[dev];
-  if (!a.s) {
-    int lo = 0, hi = 0;
-    DASP_CUDA_OK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    DASP_CUDA_OK(cudaStreamCreateWithPriority(&a.s, cudaStreamNonBlocking, lo));     // lowest priority: filler work
-    DASP_CUDA_OK(cudaEventCreateWithFlags(&a.entry, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
-      DASP_CUDA_OK(cudaEventCreateWithFlags(&a.gen_done[i], cudaEventDisableTiming));
-      DASP_CUDA_OK(cudaEventCreateWithFlags(&a.consumed[i], cudaEventDisableTiming));
-    }
-  }
-  *out = &a;
-  return DASP_OK;
-}
 std::map<PlanKey, PlanVal> g_plans;
 std::map<FbKey, cufftComplex*> g_fb;
 
@@ -867,7 +845,7 @@ void fwd_layout(const Geom& g, size_t cufft_work, FwdWs& w) {
   // transient homes for what a forward WITHOUT a backward does not keep (null *_save pointers)
   w.xsp = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.ib * kNbA));
   w.hsp = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.jb * kNbA));
-  w.fchunk = o; o += 2 * align256(sizeof(float2) * (size_t)(g.chunk * kBands * g.pair_c64()));   // double buffer
+  w.fchunk = o; o += align256(sizeof(float2) * (size_t)(g.chunk * kBands * g.pair_c64()));
   w.cufft = o; o += align256(cufft_work);
   w.total = o;
 }
@@ -902,15 +880,6 @@ void reverb_shutdown() {
   g_plans.clear();
   for (auto& kv : g_fb) cudaFree(kv.second);
   g_fb.clear();
-  for (auto& kv : g_aux) {
-    if (kv.second.s) cudaStreamDestroy(kv.second.s);
-    if (kv.second.entry) cudaEventDestroy(kv.second.entry);
-    for (int i = 0; i < 2; ++i) {
-      if (kv.second.gen_done[i]) cudaEventDestroy(kv.second.gen_done[i]);
-      if (kv.second.consumed[i]) cudaEventDestroy(kv.second.consumed[i]);
-    }
-  }
-  g_aux.clear();
 }
 
 }  // namespace dasp
@@ -1000,35 +969,12 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
   const int64_t lp = g.L + g.P;
   const int nbk = (int)g.nbk, nb = (int)g.nb, hop = (int)g.hop, P = (int)g.P, I = (int)g.ib, J = (int)g.jb;
 
-  const size_t fchunk_bytes = align256(sizeof(float2) * (size_t)(g.chunk * kBands * g.pair_c64()));
-  auto c_of = [&](int64_t item0, int64_t idx) -> float2* {
-    // kept for the backward when the caller passes f_save, else one of two transient buffers
-    return f_save ? reinterpret_cast<float2*>(f_save) + item0 * kBands * g.pair_c64()
-                  : reinterpret_cast<float2*>(base + w.fchunk + (size_t)(idx & 1) * fchunk_bytes);
-  };
-  // The spectrum generator is instruction-issue bound, everything after it bandwidth bound: generate chunk
-  // k+1 on a low-priority helper stream while the caller's stream transforms chunk k.
-  AuxStream* aux = nullptr;
-  if (spectral) {
-    if ((rc = get_aux(&aux)) != DASP_OK) return rc;
-    DASP_CUDA_OK(cudaEventRecord(aux->entry, st));             // params / previous users of the workspace
-    DASP_CUDA_OK(cudaStreamWaitEvent(aux->s, aux->entry, 0));
-  }
-  auto launch_gen = [&](int64_t item0, int64_t idx) -> int {
-    const int64_t items = (bs - item0 < g.chunk) ? bs - item0 : g.chunk;
-    if (idx >= 2 && !f_save) DASP_CUDA_OK(cudaStreamWaitEvent(aux->s, aux->consumed[idx & 1], 0));   // buffer reuse
-    dispatch_spectral((int)g.rpp, c_of(item0, idx), H1, item0, items, nb, (unsigned long long)seed, aux->s);
-    DASP_LAUNCH_OK("spectral_gen_kernel");
-    DASP_CUDA_OK(cudaEventRecord(aux->gen_done[idx & 1], aux->s));
-    return DASP_OK;
-  };
-  if (spectral && (rc = launch_gen(0, 0)) != DASP_OK) return rc;
-
-  int64_t idx = 0;
-  for (int64_t item0 = 0; item0 < bs; item0 += g.chunk, ++idx) {
+  for (int64_t item0 = 0; item0 < bs; item0 += g.chunk) {
     const int64_t items = (bs - item0 < g.chunk) ? bs - item0 : g.chunk;
     const Plans& pl = (items == g.chunk) ? pfull : prem;
-    float2* C = c_of(item0, idx);
+    // kept for the backward when the caller passes *_save buffers, transient workspace otherwise
+    float2* C = f_save ? reinterpret_cast<float2*>(f_save) + item0 * kBands * g.pair_c64()
+                       : reinterpret_cast<float2*>(base + w.fchunk);
     float2* xs = xspec_save ? (float2*)xspec_save + item0 * I * (int64_t)kNbA : (float2*)(base + w.xsp);
     float2* hs = irspec_save ? (float2*)irspec_save + item0 * J * (int64_t)kNbA : (float2*)(base + w.hsp);
     const dim3 gblk((unsigned)nbk, kBands, (unsigned)items);
@@ -1036,19 +982,15 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     // ---- IR synthesis: (left, right) taps land in the zero-initialised partition layout hs ----
     DASP_CUDA_OK(cudaMemsetAsync(hs, 0, sizeof(float2) * items * J * kNbA, st));
     if (spectral) {
-      // device noise: the filtered spectrum was drawn on the helper stream; one inverse transform
-      DASP_CUDA_OK(cudaStreamWaitEvent(st, aux->gen_done[idx & 1], 0));
-      if (item0 + g.chunk < bs) {                       // queue the next chunk's generator behind this one
-        // gen_done[(idx+1)&1] was last waited on by chunk idx-1 on `st`, which is already enqueued: safe to re-record
-        if ((rc = launch_gen(item0 + g.chunk, idx + 1)) != DASP_OK) return rc;
-      }
+      // device noise: draw the filtered spectrum directly, one inverse transform (polyphase layout)
+      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, (unsigned long long)seed, st);
+      DASP_LAUNCH_OK("spectral_gen_kernel");
       DASP_CUFFT_OK(cufftSetStream(pl.pp_c2c.h, st));
       DASP_CUFFT_OK(cufftSetWorkArea(pl.pp_c2c.h, ws_cufft));
       DASP_CUFFT_OK(cufftExecC2C(pl.pp_c2c.h, (cufftComplex*)C, (cufftComplex*)C, CUFFT_INVERSE));
       shape_ir_pp_kernel<<<dim3((unsigned)((g.leff + 255) / 256), (unsigned)items), 256, 0, st>>>(
           C, params + item0 * 25, hs, g.L, g.leff, J, (int)g.rpp, nb);
       DASP_LAUNCH_OK("shape_ir_pp_kernel");
-      if (!f_save) DASP_CUDA_OK(cudaEventRecord(aux->consumed[idx & 1], st));
     } else {
       // parity mode (caller's noise tensor) or very long IR: time-domain noise, overlap-save blocks
       if (noise) noise_pairs_layout_kernel<<<gblk, 256, 0, st>>>(noise, C, item0, nbk, nb, hop, lp);
