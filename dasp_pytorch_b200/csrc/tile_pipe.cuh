@@ -42,7 +42,13 @@ struct TileGeom {
 
 template <int S>
 struct TilePipe {
-  static_assert(S >= 3, "need >= 3 stages: computing / loading / storing");
+  static_assert(S >= 2, "need >= 2 stages");
+  // prefetch distance and the number of store groups that may still be reading shared memory when the next
+  // load is issued: with 3+ stages the stage being refilled drained two iterations ago; with 2 stages it is
+  // the stage whose store was committed at the end of the previous iteration, so that store must finish
+  // reading first (sub-microsecond, against ~10 us of compute per tile in the kernels that use S = 2)
+  static constexpr int kAhead = (S == 2) ? 1 : S - 2;
+  static constexpr int kPendingStores = (S == 2) ? 0 : 1;
   uint64_t* full;     // S mbarriers (shared memory)
   float* stages;      // S * nbuf * tile_len floats (shared memory, 128-byte aligned)
   int nbuf;           // buffers per stage
@@ -75,7 +81,7 @@ struct TilePipe {
   template <class Rows>
   __device__ __forceinline__ void prologue(const TileGeom& g, const Rows& rows) {
     if (bulk && threadIdx.x == 0) {
-      for (int j = 0; j < S - 2 && j < g.ntiles; ++j) issue_load(j, g, rows);
+      for (int j = 0; j < kAhead && j < g.ntiles; ++j) issue_load(j, g, rows);
     }
   }
 
@@ -84,11 +90,11 @@ struct TilePipe {
     const int st = seq % S;
     if (bulk) {
       if (threadIdx.x == 0) {
-        const int j = seq + (S - 2);
+        const int j = seq + kAhead;
         if (j < g.ntiles) {
-          // stage j % S was last used by tile j - S = seq - 2, whose store group was committed two
-          // iterations ago; at most the one newer group (tile seq - 1) may still be reading smem.
-          tma_store_wait_read<1>();
+          // stage j % S was last used by tile j - S; all store groups older than the newest
+          // kPendingStores have finished reading shared memory after this wait
+          tma_store_wait_read<kPendingStores>();
           issue_load(j, g, rows);
         }
       }
