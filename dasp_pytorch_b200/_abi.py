@@ -46,7 +46,6 @@ _SIGNATURES = {
     "dasp_distortion_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, P]),
     "dasp_pointwise_bwd_workspace_floats": (I64, [I64, I64]),
     "dasp_eq_tile_len": (I64, [I64]),
-    "dasp_eq_ckpt_floats": (I64, [I64, I64]),
     "dasp_eq_bwd_workspace_floats": (I64, [I64, I64]),
     "dasp_eq_fwd": (c_int, [P, P, P, P, I64, I64, I64, c_float, P]),
     "dasp_eq_bwd": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),

@@ -26,13 +26,6 @@
 //   a matrix power, not a generic 2x2 pair product.)
 // The tile-to-tile carries stay in registers; the forward stores them per tile as checkpoints.
 //
-// Packed fp32x2 math.  Measured on B200 (tools/probe/ffma2_probe.cu): scalar FFMA peaks at 21 TFMA/s, the
-// Blackwell-only packed FFMA2 (fma.rn.f32x2, __ffma2_rn) at 33 TFMA/s, and the scalar version of this kernel
-// already sat at 74 % of the scalar peak.  Every thread therefore processes a PAIR of rows -- the left and
-// right channel of a stereo item, or two neighbouring mono items -- with each float2 lane holding one row:
-// states, coefficients, matrix powers and scan operands are all (rowA, rowB) pairs, so the whole recurrence,
-// the shuffle scan and the fix-up run on FFMA2/FADD2/FMUL2.  An odd last row is paired with itself.
-//
 // Backward.  State-space adjoint (SURVEY.md A.3 restated for the sigma form): with lam = adjoint
 // state,  lam[n] = A^T lam[n+1] + (g[n],0);  gu[n] = be1*lam1[n+1] + B2*lam2[n+1] + b0*g[n];
 //   d sg = sum lam[n+1].s[n],  d q = sum lam2[n+1] s1[n],  d be1 = sum lam1[n+1] u[n],
@@ -50,7 +43,7 @@ namespace dasp {
 namespace {
 
 #ifndef DASP_EQ_E
-#define DASP_EQ_E 11
+#define DASP_EQ_E 15
 #endif
 #ifndef DASP_EQ_WARPS_PER_SM
 #define DASP_EQ_WARPS_PER_SM 24
@@ -141,57 +134,28 @@ __device__ inline M2d mpow(double sg, double q, unsigned n) {
   return r;
 }
 
-// ------------------------------------------------------------------ packed helpers
-typedef float2 f2;    // .x = row A of the pair, .y = row B
-__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ f2 mul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 addp(f2 a, f2 b) { return __fadd2_rn(a, b); }
-__device__ __forceinline__ f2 zero2() { return make_float2(0.f, 0.f); }
-struct St { f2 s1, s2; };                      // 2-vector state of one section, both rows
-struct Mp { f2 a, b, c, d; };                  // 2x2 matrix [[a,b],[c,d]] per row
-
-__device__ __forceinline__ St mv(const Mp& m, const St& v) {           // M v
-  return {fma2(m.a, v.s1, mul2(m.b, v.s2)), fma2(m.c, v.s1, mul2(m.d, v.s2))};
-}
-__device__ __forceinline__ St mtv(const Mp& m, const St& v) {          // M^T v
-  return {fma2(m.a, v.s1, mul2(m.c, v.s2)), fma2(m.b, v.s1, mul2(m.d, v.s2))};
-}
-__device__ __forceinline__ St adds(const St& x, const St& y) { return {addp(x.s1, y.s1), addp(x.s2, y.s2)}; }
-__device__ __forceinline__ f2 shfl_up2(f2 v, int d) {
-  return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
-}
-__device__ __forceinline__ f2 shfl_dn2(f2 v, int d) {
-  return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
-}
-__device__ __forceinline__ f2 shfl_at2(f2 v, int l) {
-  return make_float2(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l));
-}
-
 // ------------------------------------------------------------------ shared-memory layout
-// per-pair tables (fp32, both rows interleaved), built once per CTA.  Power-table entries per section:
-//   [0, E)      A^j            (fix-up / zero-input response)
-//   [E, E+5)    A^(E 2^s)      (Kogge-Stone steps)
-//   E+5         A^(32 E)       (warp-to-warp carry)
-//   E+6 ..      A^(E lane), lane = 0..31   (only when a CTA has more than one warp)
-template <int W>
-struct __align__(16) PairTables {
-  static constexpr int kNT = kE + 5 + 1 + (W > 1 ? 32 : 0);
-  f2 cf[kSections][6];                 // sg, q, be1, B2, b0, pad
-  Mp pw[kSections][kNT];
+// per-item tables (fp32), built once per CTA
+struct __align__(16) EqTables {
+  float cf[kSections][8];              // sg, q, be1, B2, b0, pad
+  float4 pw[kSections][kNumPowTables]; // (a,b,c,d) of the powers listed at kNumPowTables
 };
-constexpr size_t kHdrBars = 64;                                   // mbarriers
-constexpr size_t kHdrAgg = 16 * 8 * sizeof(St);                   // up to 16 scan slots x 8 warps
-template <int W>
-__host__ __device__ constexpr size_t hdr_bytes() { return ((kHdrBars + kHdrAgg + sizeof(PairTables<W>) + 127) / 128) * 128; }
+__device__ __forceinline__ const float4& pw_j(const EqTables& t, int k, int j) { return t.pw[k][j]; }            // A^j
+__device__ __forceinline__ const float4& pw_step(const EqTables& t, int k, int s) { return t.pw[k][kE + s]; }    // A^(E 2^s)
+__device__ __forceinline__ const float4& pw_lane(const EqTables& t, int k, int l) { return t.pw[k][kE + 5 + l]; }  // A^(E l)
+__device__ __forceinline__ const float4& pw_warp(const EqTables& t, int k) { return t.pw[k][kE + 5 + 32]; }       // A^(32E)
 
-template <int W>
+constexpr size_t kHdrBars = 64;                                   // S mbarriers
+constexpr size_t kHdrAgg = 16 * 2 * 8 * sizeof(float2);           // up to 16 scan slots x 8 warps (double-buffered by slot)
+constexpr size_t kHdr = ((kHdrBars + kHdrAgg + sizeof(EqTables) + 127) / 128) * 128;
+
 struct Smem {
-  uint64_t* bars; St* agg; PairTables<W>* tb; float* stages;
+  uint64_t* bars; float2* agg; EqTables* tb; float* stages;
   __device__ __forceinline__ Smem(unsigned char* base) {
     bars = reinterpret_cast<uint64_t*>(base);
-    agg = reinterpret_cast<St*>(base + kHdrBars);
-    tb = reinterpret_cast<PairTables<W>*>(base + kHdrBars + kHdrAgg);
-    stages = reinterpret_cast<float*>(base + hdr_bytes<W>());
+    agg = reinterpret_cast<float2*>(base + kHdrBars);
+    tb = reinterpret_cast<EqTables*>(base + kHdrBars + kHdrAgg);
+    stages = reinterpret_cast<float*>(base + kHdr);
   }
 };
 
@@ -200,280 +164,269 @@ struct EqParams {
   const float* gy;       // backward
   float* y;              // forward out / backward gx
   const float* params;   // (bs, 18): gain_dB, fc, Q per section, signature order
-  float* ckpt;           // (pairs, ntiles, 6, 4): section states (s1A, s1B, s2A, s2B) entering each tile
+  float* ckpt;           // (rows, ntiles, 12): section states entering each tile
   float* partial;        // (rows, 30) backward: per-row coefficient-gradient sums
   int64_t n;
-  int64_t rows;
   int chs;
   int ntiles;
   float sample_rate;
   int bulk;
 };
 
-struct PairIO {     // forward: buffer 0 = row A, 1 = row B (in place)
-  const float* a; const float* b; float* ya; float* yb;
-  __device__ __forceinline__ const float* src(int i) const { return i == 0 ? a : b; }
-  __device__ __forceinline__ float* dst(int i) const { return i == 0 ? ya : yb; }
+struct RowIO {    // forward: one buffer, in place
+  const float* src0; float* dst0;
+  __device__ __forceinline__ const float* src(int) const { return src0; }
+  __device__ __forceinline__ float* dst(int) const { return dst0; }
 };
-struct PairIOBwd {  // backward: buffers 0,1 = x rows (read only), 2,3 = gy rows -> gx rows
-  const float* xa; const float* xb; const float* ga; const float* gb; float* oa; float* ob;
-  __device__ __forceinline__ const float* src(int i) const { return i == 0 ? xa : (i == 1 ? xb : (i == 2 ? ga : gb)); }
-  __device__ __forceinline__ float* dst(int i) const { return i == 2 ? oa : (i == 3 ? ob : nullptr); }
+struct RowIOBwd { // backward: buffer 0 = x (read only), buffer 1 = gy -> gx
+  const float* x0; const float* g0; float* gx0;
+  __device__ __forceinline__ const float* src(int b) const { return b == 0 ? x0 : g0; }
+  __device__ __forceinline__ float* dst(int b) const { return b == 0 ? nullptr : gx0; }
 };
 
-// build the per-pair tables: every thread of the CTA participates; ends with __syncthreads()
-template <int W>
-__device__ void build_tables(PairTables<W>& tb, const float* params, int64_t item_a, int64_t item_b, float sample_rate) {
-  __shared__ double cfd[2][kSections][2];   // sg, q in fp64 for the matrix powers
+// build the per-item tables: every thread of the CTA participates; ends with __syncthreads()
+__device__ void build_tables(EqTables& tb, const float* params18, float sample_rate) {
+  __shared__ double cfd[kSections][2];   // sg, q in fp64 for the matrix powers
   const int tid = threadIdx.x;
-  for (int t = tid; t < 2 * kSections; t += blockDim.x) {
-    const int r = t / kSections, k = t - r * kSections;
-    const float* pp = params + (r == 0 ? item_a : item_b) * 18 + 3 * k;
-    const SigmaCoef sc = design_section((double)pp[0], (double)pp[1], (double)pp[2], (double)sample_rate, section_kind(k));
-    float* dst = reinterpret_cast<float*>(&tb.cf[k][0]) + r;
+  if (tid < kSections) {
+    const SigmaCoef sc = design_section((double)params18[3 * tid], (double)params18[3 * tid + 1],
+                                        (double)params18[3 * tid + 2], (double)sample_rate, section_kind(tid));
 #pragma unroll
-    for (int j = 0; j < 5; ++j) dst[2 * j] = (float)sc.c[j].v;
-    dst[10] = 0.f;
-    cfd[r][k][0] = sc.c[0].v;
-    cfd[r][k][1] = sc.c[1].v;
+    for (int j = 0; j < 5; ++j) tb.cf[tid][j] = (float)sc.c[j].v;
+    tb.cf[tid][5] = tb.cf[tid][6] = tb.cf[tid][7] = 0.f;
+    cfd[tid][0] = sc.c[0].v;
+    cfd[tid][1] = sc.c[1].v;
   }
   __syncthreads();
-  constexpr int NT = PairTables<W>::kNT;
-  for (int idx = tid; idx < 2 * kSections * NT; idx += blockDim.x) {
-    const int r = idx / (kSections * NT), rem = idx - r * (kSections * NT);
-    const int k = rem / NT, e = rem - k * NT;
+  for (int idx = tid; idx < kSections * kNumPowTables; idx += blockDim.x) {
+    const int k = idx / kNumPowTables, e = idx - k * kNumPowTables;
     unsigned n;
     if (e < kE) n = (unsigned)e;
     else if (e < kE + 5) n = (unsigned)kE << (e - kE);
-    else if (e == kE + 5) n = (unsigned)(kE * 32);
-    else n = (unsigned)(kE * (e - kE - 6));
-    const M2d m = mpow(cfd[r][k][0], cfd[r][k][1], n);
-    float* dst = reinterpret_cast<float*>(&tb.pw[k][e]) + r;
-    dst[0] = (float)m.a; dst[2] = (float)m.b; dst[4] = (float)m.c; dst[6] = (float)m.d;
+    else if (e < kE + 5 + 32) n = (unsigned)(kE * (e - kE - 5));
+    else n = (unsigned)(kE * 32);
+    const M2d m = mpow(cfd[k][0], cfd[k][1], n);
+    tb.pw[k][e] = make_float4((float)m.a, (float)m.b, (float)m.c, (float)m.d);
   }
   __syncthreads();
 }
 
-// ------------------------------------------------------------------ 2-state block scans (both rows packed)
-// forward in time.  v = this thread's end state after a zero-state local pass; c_tile = state entering the tile
-// (updated to the state leaving it).  Returns the state entering this thread's chunk.
+// ------------------------------------------------------------------ 2-state block scans
+__device__ __forceinline__ float2 mv(const float4& m, float2 v) {          // M v
+  return make_float2(fmaf(m.x, v.x, m.y * v.y), fmaf(m.z, v.x, m.w * v.y));
+}
+__device__ __forceinline__ float2 mtv(const float4& m, float2 v) {         // M^T v
+  return make_float2(fmaf(m.x, v.x, m.z * v.y), fmaf(m.y, v.x, m.w * v.y));
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+
+// forward in time: v = this thread's end state after a zero-state local pass; c_tile = state entering
+// the tile (updated to the state leaving it).  Returns the state entering this thread's chunk.
 template <int W>
-__device__ __forceinline__ St scan_fwd2(St v, St& c_tile, const PairTables<W>& tb, int k, St* agg, int lane, int warp) {
-  if (W == 1) {
-    // single warp: fold the tile carry into lane 0 (v0 += A^E c), then the inclusive scan yields every
-    // thread's TRUE end state and the incoming state is simply the left neighbour's
-    if (lane == 0) v = adds(v, mv(tb.pw[k][kE + 0], c_tile));
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      St u = {shfl_up2(v.s1, 1 << s), shfl_up2(v.s2, 1 << s)};
-      if (lane >= (1 << s)) v = adds(v, mv(tb.pw[k][kE + s], u));
-    }
-    St in = {shfl_up2(v.s1, 1), shfl_up2(v.s2, 1)};
-    if (lane == 0) in = c_tile;
-    c_tile = {shfl_at2(v.s1, 31), shfl_at2(v.s2, 31)};
-    return in;
-  }
+__device__ __forceinline__ float2 scan_fwd2(float2 v, float2& c_tile, const EqTables& tb, int k, float2* agg,
+                                            int lane, int warp) {
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
-    St u = {shfl_up2(v.s1, 1 << s), shfl_up2(v.s2, 1 << s)};
-    if (lane >= (1 << s)) v = adds(v, mv(tb.pw[k][kE + s], u));
+    float2 u;
+    u.x = __shfl_up_sync(0xffffffffu, v.x, 1 << s);
+    u.y = __shfl_up_sync(0xffffffffu, v.y, 1 << s);
+    if (lane >= (1 << s)) v = add2(v, mv(pw_step(tb, k, s), u));
   }
-  St excl = {shfl_up2(v.s1, 1), shfl_up2(v.s2, 1)};
-  if (lane == 0) excl = {zero2(), zero2()};
-  if (lane == 31) agg[warp] = v;
-  __syncthreads();
-  St c = c_tile, c_warp = c_tile;
-  const Mp wm = tb.pw[k][kE + 5];
+  float2 excl;
+  excl.x = __shfl_up_sync(0xffffffffu, v.x, 1);
+  excl.y = __shfl_up_sync(0xffffffffu, v.y, 1);
+  if (lane == 0) excl = make_float2(0.f, 0.f);
+  float2 c_warp = c_tile;
+  const float4 wm = pw_warp(tb, k);
+  if (W > 1) {
+    if (lane == 31) agg[warp] = v;
+    __syncthreads();
+    float2 c = c_tile;
 #pragma unroll
-  for (int w = 0; w < W; ++w) {
-    if (w == warp) c_warp = c;
-    c = adds(mv(wm, c), agg[w]);
+    for (int w = 0; w < W; ++w) {
+      if (w == warp) c_warp = c;
+      c = add2(mv(wm, c), agg[w]);
+    }
+    c_tile = c;
+  } else {
+    float2 tot;
+    tot.x = __shfl_sync(0xffffffffu, v.x, 31);
+    tot.y = __shfl_sync(0xffffffffu, v.y, 31);
+    c_tile = add2(mv(wm, c_tile), tot);
   }
-  c_tile = c;
-  return adds(excl, mv(tb.pw[k][kE + 6 + lane], c_warp));
+  return add2(excl, mv(pw_lane(tb, k, lane), c_warp));
 }
 
 // reverse in time (adjoint): v = adjoint state at this thread's first sample after a zero-terminal local
 // reverse pass; c_tile = adjoint state at the first sample of the NEXT tile.  Uses transposed powers.
 template <int W>
-__device__ __forceinline__ St scan_rev2(St v, St& c_tile, const PairTables<W>& tb, int k, St* agg, int lane, int warp) {
-  if (W == 1) {
-    if (lane == 31) v = adds(v, mtv(tb.pw[k][kE + 0], c_tile));
-#pragma unroll
-    for (int s = 0; s < 5; ++s) {
-      St u = {shfl_dn2(v.s1, 1 << s), shfl_dn2(v.s2, 1 << s)};
-      if (lane + (1 << s) < 32) v = adds(v, mtv(tb.pw[k][kE + s], u));
-    }
-    St in = {shfl_dn2(v.s1, 1), shfl_dn2(v.s2, 1)};
-    if (lane == 31) in = c_tile;
-    c_tile = {shfl_at2(v.s1, 0), shfl_at2(v.s2, 0)};
-    return in;
-  }
+__device__ __forceinline__ float2 scan_rev2(float2 v, float2& c_tile, const EqTables& tb, int k, float2* agg,
+                                            int lane, int warp) {
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
-    St u = {shfl_dn2(v.s1, 1 << s), shfl_dn2(v.s2, 1 << s)};
-    if (lane + (1 << s) < 32) v = adds(v, mtv(tb.pw[k][kE + s], u));
+    float2 u;
+    u.x = __shfl_down_sync(0xffffffffu, v.x, 1 << s);
+    u.y = __shfl_down_sync(0xffffffffu, v.y, 1 << s);
+    if (lane + (1 << s) < 32) v = add2(v, mtv(pw_step(tb, k, s), u));
   }
-  St excl = {shfl_dn2(v.s1, 1), shfl_dn2(v.s2, 1)};
-  if (lane == 31) excl = {zero2(), zero2()};
-  if (lane == 0) agg[warp] = v;
-  __syncthreads();
-  St c = c_tile, c_warp = c_tile;
-  const Mp wm = tb.pw[k][kE + 5];
+  float2 excl;
+  excl.x = __shfl_down_sync(0xffffffffu, v.x, 1);
+  excl.y = __shfl_down_sync(0xffffffffu, v.y, 1);
+  if (lane == 31) excl = make_float2(0.f, 0.f);
+  float2 c_warp = c_tile;
+  const float4 wm = pw_warp(tb, k);
+  if (W > 1) {
+    if (lane == 0) agg[warp] = v;
+    __syncthreads();
+    float2 c = c_tile;
 #pragma unroll
-  for (int w = W - 1; w >= 0; --w) {
-    if (w == warp) c_warp = c;
-    c = adds(mtv(wm, c), agg[w]);
+    for (int w = W - 1; w >= 0; --w) {
+      if (w == warp) c_warp = c;
+      c = add2(mtv(wm, c), agg[w]);
+    }
+    c_tile = c;
+  } else {
+    float2 tot;
+    tot.x = __shfl_sync(0xffffffffu, v.x, 0);
+    tot.y = __shfl_sync(0xffffffffu, v.y, 0);
+    c_tile = add2(mtv(wm, c_tile), tot);
   }
-  c_tile = c;
   // distance from the first sample of thread lane+1 to the first sample of the next warp: (31-lane) chunks
-  return adds(excl, mtv(tb.pw[k][kE + 6 + (31 - lane)], c_warp));
+  return add2(excl, mtv(pw_lane(tb, k, 31 - lane), c_warp));
 }
 
-struct Cf { f2 sg, q, be1, B2, b0; };
-template <int W>
-__device__ __forceinline__ Cf load_cf(const PairTables<W>& tb, int k) {
-  return {tb.cf[k][0], tb.cf[k][1], tb.cf[k][2], tb.cf[k][3], tb.cf[k][4]};
+struct Cf { float sg, q, be1, B2, b0; };
+__device__ __forceinline__ Cf load_cf(const EqTables& tb, int k) {
+  const float4 a = *reinterpret_cast<const float4*>(&tb.cf[k][0]);
+  return {a.x, a.y, a.z, a.w, tb.cf[k][4]};
 }
 
-// zero-state local pass of one section over the thread's E samples (in place); returns the end state
-__device__ __forceinline__ St local_pass(f2 (&v)[kE], const Cf& c) {
-  f2 s1 = zero2(), s2 = zero2();
+// zero-state local pass of section k over the thread's E samples (in place); returns the end state
+__device__ __forceinline__ float2 local_pass(float (&v)[kE], const Cf& c) {
+  float s1 = 0.f, s2 = 0.f;
 #pragma unroll
   for (int j = 0; j < kE; ++j) {
-    const f2 u = v[j];
-    v[j] = fma2(c.b0, u, s1);
-    const f2 t1 = fma2(c.be1, u, fma2(c.sg, s1, s2));
-    s2 = fma2(c.B2, u, fma2(c.q, s1, mul2(c.sg, s2)));
+    const float u = v[j];
+    v[j] = fmaf(c.b0, u, s1);
+    const float t1 = fmaf(c.be1, u, fmaf(c.sg, s1, s2));
+    s2 = fmaf(c.B2, u, fmaf(c.q, s1, c.sg * s2));
     s1 = t1;
   }
-  return {s1, s2};
-}
-
-__device__ __forceinline__ void load_pair(f2 (&v)[kE], const float* a, const float* b, int64_t n0, int64_t n) {
-#pragma unroll
-  for (int j = 0; j < kE; ++j) v[j] = (n0 + j < n) ? make_float2(a[j], b[j]) : zero2();
+  return make_float2(s1, s2);
 }
 
 // =============================================================================== forward
 template <int W>
 __global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem<W> sm(smem_raw);
-  PairTables<W>& tb = *sm.tb;
-  const int64_t row_a = 2 * (int64_t)blockIdx.x;
-  const bool has_b = row_a + 1 < p.rows;
-  const int64_t row_b = has_b ? row_a + 1 : row_a;
+  Smem sm(smem_raw);
+  EqTables& tb = *sm.tb;
+  const int row = blockIdx.x, item = row / p.chs;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile_len = W * 32 * kE;
 
-  build_tables<W>(tb, p.params, row_a / p.chs, row_b / p.chs, p.sample_rate);
+  build_tables(tb, p.params + (int64_t)item * 18, p.sample_rate);
 
   TileGeom g{p.n, tile_len, p.ntiles, false};
-  PairIO rows{p.x + row_a * p.n, p.x + row_b * p.n, p.y + row_a * p.n, has_b ? p.y + row_b * p.n : nullptr};
+  RowIO rows{p.x + (int64_t)row * p.n, p.y + (int64_t)row * p.n};
   TilePipe<kStages> pipe;
-  pipe.init(sm.bars, sm.stages, 2, tile_len, p.bulk != 0);
+  pipe.init(sm.bars, sm.stages, 1, tile_len, p.bulk != 0);
   pipe.prologue(g, rows);
 
-  St carry[kSections];
+  float2 carry[kSections];
 #pragma unroll
-  for (int k = 0; k < kSections; ++k) carry[k] = {zero2(), zero2()};
+  for (int k = 0; k < kSections; ++k) carry[k] = make_float2(0.f, 0.f);
   const int off = threadIdx.x * kE;
 
   for (int i = 0; i < p.ntiles; ++i) {
     pipe.acquire(i, g, rows);
-    float* ba = pipe.buf(i % kStages, 0) + off;
-    float* bb = pipe.buf(i % kStages, 1) + off;
+    float* buf = pipe.buf(i % kStages, 0) + off;
     const int64_t n0 = (int64_t)i * tile_len + off;
     if (p.ckpt && threadIdx.x == 0) {
-      St* ck = reinterpret_cast<St*>(p.ckpt + ((int64_t)blockIdx.x * p.ntiles + i) * 24);
+      float2* ck = reinterpret_cast<float2*>(p.ckpt + ((int64_t)row * p.ntiles + i) * 12);
 #pragma unroll
       for (int k = 0; k < kSections; ++k) ck[k] = carry[k];
     }
-    f2 v[kE];
-    load_pair(v, ba, bb, n0, p.n);
+    float v[kE];
+#pragma unroll
+    for (int j = 0; j < kE; ++j) v[j] = (n0 + j < p.n) ? buf[j] : 0.f;
 
 #pragma unroll
     for (int k = 0; k < kSections; ++k) {
-      const Cf c = load_cf<W>(tb, k);
-      const St end = local_pass(v, c);
-      const St cin = scan_fwd2<W>(end, carry[k], tb, k, sm.agg + ((i * kSections + k) & 1) * 8, lane, warp);
+      const Cf c = load_cf(tb, k);
+      const float2 end = local_pass(v, c);
+      const float2 cin = scan_fwd2<W>(end, carry[k], tb, k, sm.agg + ((i * kSections + k) & 1) * 8, lane, warp);
 #pragma unroll
       for (int j = 0; j < kE; ++j) {
-        const Mp& m = tb.pw[k][j];                       // y[j] += (A^j c_in)_1
-        v[j] = fma2(m.a, cin.s1, fma2(m.b, cin.s2, v[j]));
+        const float4 m = pw_j(tb, k, j);                 // y[j] += (A^j c_in)_1
+        v[j] = fmaf(m.x, cin.x, fmaf(m.y, cin.y, v[j]));
       }
     }
 #pragma unroll
-    for (int j = 0; j < kE; ++j) { ba[j] = v[j].x; bb[j] = v[j].y; }
+    for (int j = 0; j < kE; ++j) buf[j] = v[j];
     pipe.release(i, g, rows);
   }
   pipe.drain();
 }
 
 // =============================================================================== backward
-constexpr int kBwdStages = 2;
-
 template <int W>
 __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem<W> sm(smem_raw);
-  PairTables<W>& tb = *sm.tb;
-  __shared__ double red[W][kSections * 5 * 2];
-  const int64_t row_a = 2 * (int64_t)blockIdx.x;
-  const bool has_b = row_a + 1 < p.rows;
-  const int64_t row_b = has_b ? row_a + 1 : row_a;
+  Smem sm(smem_raw);
+  EqTables& tb = *sm.tb;
+  __shared__ double red[W][kSections * 5];
+  const int row = blockIdx.x, item = row / p.chs;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tile_len = W * 32 * kE;
-  const int nthr = W * 32;
 
-  build_tables<W>(tb, p.params, row_a / p.chs, row_b / p.chs, p.sample_rate);
+  build_tables(tb, p.params + (int64_t)item * 18, p.sample_rate);
 
   TileGeom g{p.n, tile_len, p.ntiles, true};
-  PairIOBwd rows{p.x + row_a * p.n, p.x + row_b * p.n, p.gy + row_a * p.n, p.gy + row_b * p.n,
-                 p.y + row_a * p.n, has_b ? p.y + row_b * p.n : nullptr};
-  TilePipe<kBwdStages> pipe;
-  pipe.init(sm.bars, sm.stages, 4, tile_len, p.bulk != 0);
+  RowIOBwd rows{p.x + (int64_t)row * p.n, p.gy + (int64_t)row * p.n, p.y + (int64_t)row * p.n};
+  TilePipe<kStages> pipe;
+  pipe.init(sm.bars, sm.stages, 2, tile_len, p.bulk != 0);
   pipe.prologue(g, rows);
-  // behind the pipeline stages: thread-private scratch for the inputs of sections 1..5 (u_1..u_5, packed pairs)
-  // and the 30 running sums per thread, laid out [sum][thread] so that warps touch consecutive words
-  f2* scratch = reinterpret_cast<f2*>(sm.stages + (size_t)kBwdStages * 4 * tile_len);
-  f2* accs = scratch + (size_t)(kSections - 1) * tile_len;
-  for (int q = 0; q < kSections * 5; ++q) accs[q * nthr + threadIdx.x] = zero2();
+  // thread-private scratch for the inputs of sections 1..5 (u_1..u_5), behind the pipeline stages
+  float* scratch = sm.stages + (size_t)kStages * 2 * tile_len;
 
-  St adj[kSections];          // adjoint state at the first sample of the next tile, per section
+  float2 adj[kSections];          // adjoint state at the first sample of the next tile, per section
+  float acc[kSections][5];
 #pragma unroll
-  for (int k = 0; k < kSections; ++k) adj[k] = {zero2(), zero2()};
+  for (int k = 0; k < kSections; ++k) {
+    adj[k] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < 5; ++q) acc[k][q] = 0.f;
+  }
   const int off = threadIdx.x * kE;
 
   for (int i = 0; i < p.ntiles; ++i) {
     pipe.acquire(i, g, rows);
-    const int st = i % kBwdStages;
+    const int st = i % kStages;
     const int tile = g.tile_of(i);
     const int64_t n0 = (int64_t)tile * tile_len + off;
-    const float* xa = pipe.buf(st, 0) + off;
-    const float* xb = pipe.buf(st, 1) + off;
-    float* ga = pipe.buf(st, 2) + off;
-    float* gb = pipe.buf(st, 3) + off;
-    const St* ck = reinterpret_cast<const St*>(p.ckpt + ((int64_t)blockIdx.x * p.ntiles + tile) * 24);
+    const float* xb = pipe.buf(st, 0) + off;
+    float* gb = pipe.buf(st, 1) + off;
+    const float2* ck = reinterpret_cast<const float2*>(p.ckpt + ((int64_t)row * p.ntiles + tile) * 12);
 
     // ---- phase F: recompute the section inputs u_1..u_5 and every section's incoming state ----
-    St cin[kSections];
+    float2 cin[kSections];
     {
-      f2 v[kE];
-      load_pair(v, xa, xb, n0, p.n);
+      float v[kE];
+#pragma unroll
+      for (int j = 0; j < kE; ++j) v[j] = (n0 + j < p.n) ? xb[j] : 0.f;
 #pragma unroll
       for (int k = 0; k < kSections; ++k) {
-        const Cf c = load_cf<W>(tb, k);
-        const St end = local_pass(v, c);
-        St ct = ck[k];
+        const Cf c = load_cf(tb, k);
+        const float2 end = local_pass(v, c);
+        float2 ct = ck[k];
         cin[k] = scan_fwd2<W>(end, ct, tb, k, sm.agg + (2 * k + 0) * 8, lane, warp);
         if (k < kSections - 1) {
-          f2* uk = scratch + (size_t)k * tile_len + off;
+          float* uk = scratch + (size_t)k * tile_len + off;
 #pragma unroll
           for (int j = 0; j < kE; ++j) {
-            const Mp& m = tb.pw[k][j];
-            v[j] = fma2(m.a, cin[k].s1, fma2(m.b, cin[k].s2, v[j]));
+            const float4 m = pw_j(tb, k, j);
+            v[j] = fmaf(m.x, cin[k].x, fmaf(m.y, cin[k].y, v[j]));
             uk[j] = v[j];
           }
         }
@@ -481,85 +434,78 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
     }
 
     // ---- phase B: unwind the sections 6 -> 1 ----
-    f2 gq[kE];
-    load_pair(gq, ga, gb, n0, p.n);
+    float gq[kE];
+#pragma unroll
+    for (int j = 0; j < kE; ++j) gq[j] = (n0 + j < p.n) ? gb[j] : 0.f;
 #pragma unroll
     for (int k = kSections - 1; k >= 0; --k) {
-      const Cf c = load_cf<W>(tb, k);
-      f2 u[kE], s1[kE], s2[kE];
-      if (k == 0) {
-        load_pair(u, xa, xb, n0, p.n);
-      } else {
-        const f2* uk = scratch + (size_t)(k - 1) * tile_len + off;
+      const Cf c = load_cf(tb, k);
+      float u[kE], s1[kE], s2[kE];
+      {
+        const float* uk = (k == 0) ? xb : (scratch + (size_t)(k - 1) * tile_len + off);
 #pragma unroll
-        for (int j = 0; j < kE; ++j) u[j] = (n0 + j < p.n) ? uk[j] : zero2();
+        for (int j = 0; j < kE; ++j) u[j] = (n0 + j < p.n) ? uk[j] : 0.f;
       }
       {  // true-state forward pass: s[j] = state BEFORE sample j
-        f2 a1 = cin[k].s1, a2 = cin[k].s2;
+        float a1 = cin[k].x, a2 = cin[k].y;
 #pragma unroll
         for (int j = 0; j < kE; ++j) {
           s1[j] = a1; s2[j] = a2;
-          const f2 t1 = fma2(c.be1, u[j], fma2(c.sg, a1, a2));
-          a2 = fma2(c.B2, u[j], fma2(c.q, a1, mul2(c.sg, a2)));
+          const float t1 = fmaf(c.be1, u[j], fmaf(c.sg, a1, a2));
+          a2 = fmaf(c.B2, u[j], fmaf(c.q, a1, c.sg * a2));
           a1 = t1;
         }
       }
-      St agg_v;
+      float2 agg_v;
       {  // zero-terminal reverse pass: only the value reaching the chunk's first sample is needed
-        f2 l1 = zero2(), l2 = zero2();
+        float l1 = 0.f, l2 = 0.f;
 #pragma unroll
         for (int j = kE - 1; j >= 0; --j) {
-          const f2 t1 = fma2(c.sg, l1, fma2(c.q, l2, gq[j]));
-          l2 = fma2(c.sg, l2, l1);
+          const float t1 = fmaf(c.sg, l1, fmaf(c.q, l2, gq[j]));
+          l2 = fmaf(c.sg, l2, l1);
           l1 = t1;
         }
-        agg_v = {l1, l2};
+        agg_v = make_float2(l1, l2);
       }
-      const St din = scan_rev2<W>(agg_v, adj[k], tb, k, sm.agg + (2 * k + 1) * 8, lane, warp);
-      f2 a0 = zero2(), a1s = zero2(), a2s = zero2(), a3 = zero2(), a4 = zero2();
+      const float2 din = scan_rev2<W>(agg_v, adj[k], tb, k, sm.agg + (2 * k + 1) * 8, lane, warp);
       {  // final reverse pass with the true terminal adjoint state
-        f2 l1 = din.s1, l2 = din.s2;      // lambda[n+1] while processing sample n
+        float l1 = din.x, l2 = din.y;      // lambda[n+1] while processing sample n
 #pragma unroll
         for (int j = kE - 1; j >= 0; --j) {
-          const f2 gj = gq[j];
-          a0 = fma2(l1, s1[j], fma2(l2, s2[j], a0));
-          a1s = fma2(l2, s1[j], a1s);
-          a2s = fma2(l1, u[j], a2s);
-          a3 = fma2(l2, u[j], a3);
-          a4 = fma2(gj, u[j], a4);
-          gq[j] = fma2(c.be1, l1, fma2(c.B2, l2, mul2(c.b0, gj)));
-          const f2 t1 = fma2(c.sg, l1, fma2(c.q, l2, gj));
-          l2 = fma2(c.sg, l2, l1);
+          const float gj = gq[j];
+          acc[k][0] = fmaf(l1, s1[j], fmaf(l2, s2[j], acc[k][0]));
+          acc[k][1] = fmaf(l2, s1[j], acc[k][1]);
+          acc[k][2] = fmaf(l1, u[j], acc[k][2]);
+          acc[k][3] = fmaf(l2, u[j], acc[k][3]);
+          acc[k][4] = fmaf(gj, u[j], acc[k][4]);
+          gq[j] = fmaf(c.be1, l1, fmaf(c.B2, l2, c.b0 * gj));
+          const float t1 = fmaf(c.sg, l1, fmaf(c.q, l2, gj));
+          l2 = fmaf(c.sg, l2, l1);
           l1 = t1;
         }
       }
-      f2* ac = accs + (size_t)(k * 5) * nthr + threadIdx.x;
-      ac[0 * nthr] = addp(ac[0 * nthr], a0);
-      ac[1 * nthr] = addp(ac[1 * nthr], a1s);
-      ac[2 * nthr] = addp(ac[2 * nthr], a2s);
-      ac[3 * nthr] = addp(ac[3 * nthr], a3);
-      ac[4 * nthr] = addp(ac[4 * nthr], a4);
     }
 #pragma unroll
-    for (int j = 0; j < kE; ++j) { ga[j] = gq[j].x; gb[j] = gq[j].y; }
+    for (int j = 0; j < kE; ++j) gb[j] = gq[j];
     pipe.release(i, g, rows);
   }
   pipe.drain();
 
-  // ---- deterministic block reduction of the 30 sums per row (fp64) ----
-  for (int q = 0; q < kSections * 5; ++q) {
-    const f2 v = accs[q * nthr + threadIdx.x];
-    const double sa = warp_sum((double)v.x), sb = warp_sum((double)v.y);
-    if (lane == 0) { red[warp][2 * q] = sa; red[warp][2 * q + 1] = sb; }
+  // ---- deterministic block reduction of the 30 sums (fp64), one partial row per CTA ----
+#pragma unroll
+  for (int k = 0; k < kSections; ++k) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      const double s = warp_sum((double)acc[k][q]);
+      if (lane == 0) red[warp][k * 5 + q] = s;
+    }
   }
   __syncthreads();
-  if (threadIdx.x < kSections * 5 * 2) {
+  if (threadIdx.x < kSections * 5) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < W; ++w) s += red[w][threadIdx.x];
-    const int q = threadIdx.x >> 1, r = threadIdx.x & 1;
-    if (r == 0) p.partial[row_a * 30 + q] = (float)s;
-    else if (has_b) p.partial[row_b * 30 + q] = (float)s;
+    p.partial[(int64_t)row * 30 + threadIdx.x] = (float)s;
   }
 }
 
@@ -588,32 +534,28 @@ __global__ void eq_param_grad_kernel(const float* __restrict__ partial, const fl
 }
 
 // ---- host side -----------------------------------------------------------------------------
-int pick_warps(int64_t pairs) {
+int pick_warps(int64_t rows) {
   const int64_t want = (int64_t)DASP_EQ_WARPS_PER_SM * sm_count();
   int w = 1;
-  while (w < 4 && pairs * w < want) w *= 2;
+  while (w < 4 && rows * w < want) w *= 2;
   return w;
 }
-template <int W> size_t smem_fwd() { return hdr_bytes<W>() + (size_t)kStages * 2 * (W * 32 * kE) * 4; }
-template <int W> size_t smem_bwd() {
-  const size_t tile = (size_t)W * 32 * kE;
-  return hdr_bytes<W>() + (size_t)kBwdStages * 4 * tile * 4 + (size_t)(kSections - 1) * tile * 8 +
-         (size_t)kSections * 5 * (W * 32) * 8;
-}
+size_t smem_fwd(int w) { return kHdr + (size_t)kStages * 1 * (w * 32 * kE) * 4; }
+size_t smem_bwd(int w) { return kHdr + (size_t)(kStages * 2 + (kSections - 1)) * (w * 32 * kE) * 4; }
 
 template <int W>
-int launch_fwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
-  const size_t smem = smem_fwd<W>();
+int launch_fwd_w(const EqParams& p, int64_t rows, cudaStream_t st) {
+  const size_t smem = smem_fwd(W);
   DASP_CUDA_OK(cudaFuncSetAttribute(eq_fwd_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  eq_fwd_kernel<W><<<(unsigned)pairs, W * 32, smem, st>>>(p);
+  eq_fwd_kernel<W><<<(unsigned)rows, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("eq_fwd_kernel");
   return DASP_OK;
 }
 template <int W>
-int launch_bwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
-  const size_t smem = smem_bwd<W>();
+int launch_bwd_w(const EqParams& p, int64_t rows, cudaStream_t st) {
+  const size_t smem = smem_bwd(W);
   DASP_CUDA_OK(cudaFuncSetAttribute(eq_bwd_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  eq_bwd_kernel<W><<<(unsigned)pairs, W * 32, smem, st>>>(p);
+  eq_bwd_kernel<W><<<(unsigned)rows, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("eq_bwd_kernel");
   return DASP_OK;
 }
@@ -625,12 +567,7 @@ using namespace dasp;
 
 extern "C" {
 
-int64_t dasp_eq_tile_len(int64_t rows) { return (int64_t)pick_warps((rows + 1) / 2) * 32 * kE; }
-int64_t dasp_eq_ckpt_floats(int64_t rows, int64_t n) {
-  const int64_t tile = dasp_eq_tile_len(rows);
-  const int64_t ntiles = n > 0 ? (n + tile - 1) / tile : 1;
-  return ((rows + 1) / 2) * ntiles * 24;
-}
+int64_t dasp_eq_tile_len(int64_t rows) { return (int64_t)pick_warps(rows) * 32 * kE; }
 int64_t dasp_eq_bwd_workspace_floats(int64_t bs, int64_t chs) { return bs * chs * 30; }
 
 int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int64_t bs, int64_t chs, int64_t n,
@@ -640,19 +577,19 @@ int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int6
   if (bs == 0 || n == 0) return DASP_OK;
   DASP_REQUIRE(x && params && y, "eq fwd: null pointer");
   DASP_REQUIRE(sample_rate > 0.f, "eq fwd: sample_rate must be positive");
-  const int64_t rows = bs * chs, pairs = (rows + 1) / 2;
-  DASP_REQUIRE(pairs < (1ll << 31), "eq fwd: too many rows");
-  const int w = pick_warps(pairs);
+  const int64_t rows = bs * chs;
+  DASP_REQUIRE(rows < (1ll << 31), "eq fwd: too many rows");
+  const int w = pick_warps(rows);
   const int tile_len = w * 32 * kE;
   EqParams p{};
-  p.x = x; p.y = y; p.params = params; p.ckpt = ckpt; p.n = n; p.rows = rows; p.chs = (int)chs;
+  p.x = x; p.y = y; p.params = params; p.ckpt = ckpt; p.n = n; p.chs = (int)chs;
   p.ntiles = (int)((n + tile_len - 1) / tile_len); p.sample_rate = sample_rate;
   p.bulk = (n % 4 == 0) && aligned16(x) && aligned16(y);
   cudaStream_t st = (cudaStream_t)stream;
   switch (w) {
-    case 1: return launch_fwd_w<1>(p, pairs, st);
-    case 2: return launch_fwd_w<2>(p, pairs, st);
-    default: return launch_fwd_w<4>(p, pairs, st);
+    case 1: return launch_fwd_w<1>(p, rows, st);
+    case 2: return launch_fwd_w<2>(p, rows, st);
+    default: return launch_fwd_w<4>(p, rows, st);
   }
 }
 
@@ -666,23 +603,23 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
   DASP_REQUIRE(gparams != nullptr, "eq bwd: null gparams");
   if (n == 0) { DASP_CUDA_OK(cudaMemsetAsync(gparams, 0, sizeof(float) * 18 * bs, st)); return DASP_OK; }
   DASP_REQUIRE(gy && x && params && ckpt && gx, "eq bwd: null pointer");
-  const int64_t rows = bs * chs, pairs = (rows + 1) / 2;
-  DASP_REQUIRE(pairs < (1ll << 31), "eq bwd: too many rows");
+  const int64_t rows = bs * chs;
+  DASP_REQUIRE(rows < (1ll << 31), "eq bwd: too many rows");
   if (ws == nullptr || ws_floats < rows * 30) {
     set_error("eq bwd: workspace needs %lld floats, got %lld", (long long)(rows * 30), (long long)ws_floats);
     return DASP_ERR_WORKSPACE;
   }
-  const int w = pick_warps(pairs);
+  const int w = pick_warps(rows);
   const int tile_len = w * 32 * kE;
   EqParams p{};
   p.x = x; p.gy = gy; p.y = gx; p.params = params; p.ckpt = const_cast<float*>(ckpt); p.partial = ws; p.n = n;
-  p.rows = rows; p.chs = (int)chs; p.ntiles = (int)((n + tile_len - 1) / tile_len); p.sample_rate = sample_rate;
+  p.chs = (int)chs; p.ntiles = (int)((n + tile_len - 1) / tile_len); p.sample_rate = sample_rate;
   p.bulk = (n % 4 == 0) && aligned16(x) && aligned16(gy) && aligned16(gx);
   int rc;
   switch (w) {
-    case 1: rc = launch_bwd_w<1>(p, pairs, st); break;
-    case 2: rc = launch_bwd_w<2>(p, pairs, st); break;
-    default: rc = launch_bwd_w<4>(p, pairs, st); break;
+    case 1: rc = launch_bwd_w<1>(p, rows, st); break;
+    case 2: rc = launch_bwd_w<2>(p, rows, st); break;
+    default: rc = launch_bwd_w<4>(p, rows, st); break;
   }
   if (rc != DASP_OK) return rc;
   const int64_t tot = bs * kSections;

@@ -81,12 +81,10 @@ int dasp_dynamics_bwd(int kind, const float* gy, const float* x, const float* th
  *      signal.biquad signal.py:242-306 and signal.sosfilt_via_fsm signal.py:136-166) ------
  * params is [bs][18] = (gain_dB, cutoff_Hz, Q) for low shelf, band0..band3, high shelf, i.e. the
  * 18 tensors of the reference signature stacked in order; the same filter is applied to every
- * channel of an item (signal.py:157-158).  Rows are processed in pairs (packed fp32x2 math).  ckpt (fwd:
- * optional out, bwd: in) holds the section states of a row pair at every tile boundary:
- * dasp_eq_ckpt_floats(bs*chs, n) floats.
+ * channel of an item (signal.py:157-158).  ckpt (fwd: optional out, bwd: in) holds the twelve
+ * section states at every tile boundary: bs*chs * ceil(n / dasp_eq_tile_len(bs*chs)) * 12 floats.
  * gparams is [bs][18]; ws needs dasp_eq_bwd_workspace_floats(bs, chs) floats. */
 int64_t dasp_eq_tile_len(int64_t rows);
-int64_t dasp_eq_ckpt_floats(int64_t rows, int64_t n);   /* floats of `ckpt` for rows = bs*chs rows of n samples */
 int64_t dasp_eq_bwd_workspace_floats(int64_t bs, int64_t chs);
 int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int64_t bs, int64_t chs,
                 int64_t n, float sample_rate, void* stream);
