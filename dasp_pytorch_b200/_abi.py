@@ -45,6 +45,13 @@ _SIGNATURES = {
     "dasp_distortion_fwd": (c_int, [P, P, P, I64, I64, P]),
     "dasp_distortion_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, P]),
     "dasp_pointwise_bwd_workspace_floats": (I64, [I64, I64]),
+    "dasp_stereo_bwd_workspace_floats": (I64, [I64, I64]),
+    "dasp_widener_fwd": (c_int, [P, P, P, I64, I64, P]),
+    "dasp_widener_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, P]),
+    "dasp_panner_fwd": (c_int, [P, P, P, I64, I64, I64, P]),
+    "dasp_panner_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
+    "dasp_bus_fwd": (c_int, [P, P, P, I64, I64, I64, P]),
+    "dasp_bus_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "dasp_eq_tile_len": (I64, [I64]),
     "dasp_eq_bwd_workspace_floats": (I64, [I64, I64]),
     "dasp_eq_fwd": (c_int, [P, P, P, P, I64, I64, I64, c_float, P]),

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 # experiments: DASP_NVCC_DEFS="-DDASP_EQ_E=7" DASP_LIB_SUFFIX=_e7 python -m dasp_pytorch_b200.build --force
 LIB = os.path.join(HERE, f"libdasp_b200{os.environ.get('DASP_LIB_SUFFIX', '')}.so")
-SOURCES = ["abi.cu", "pointwise.cu", "dynamics.cu", "biquad.cu", "reverb.cu"]
+SOURCES = ["abi.cu", "pointwise.cu", "stereo.cu", "dynamics.cu", "biquad.cu", "reverb.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

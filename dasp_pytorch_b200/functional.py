@@ -24,6 +24,9 @@ from dasp_pytorch_b200._abi import DaspError, check, ptr, stream_ptr
 __all__ = [
     "gain",
     "distortion",
+    "stereo_widener",
+    "stereo_panner",
+    "stereo_bus",
     "parametric_eq",
     "compressor",
     "expander",
@@ -171,6 +174,115 @@ def distortion(x: torch.Tensor, sample_rate: int, drive_db: torch.Tensor):
     d = _param(drive_db, bs * chs, xf, "drive_db")
     y = _PointwiseFn.apply(xf, d.contiguous(), "distortion", bs * chs, n)
     return y.to(dt)
+
+
+# --------------------------------------------------------------------------------------
+# stereo mixing processors
+# --------------------------------------------------------------------------------------
+
+
+class _StereoFn(torch.autograd.Function):
+    """kind: 'widener' | 'panner' | 'bus' -- streaming mixes with one scalar parameter per row."""
+
+    @staticmethod
+    def forward(ctx, x, p, kind):
+        lib = _abi.lib()
+        dev = x.device
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            if kind == "widener":
+                bs, _, n = x.shape
+                y = torch.empty_like(x)
+                check(lib.dasp_widener_fwd(ptr(x), ptr(p), ptr(y), bs, n, st), "dasp_widener_fwd")
+            elif kind == "panner":
+                bs, tracks, n = x.shape
+                y = torch.empty(bs, 2, tracks, n, dtype=torch.float32, device=dev)
+                check(lib.dasp_panner_fwd(ptr(x), ptr(p), ptr(y), bs, tracks, n, st), "dasp_panner_fwd")
+            else:
+                bs, _, tracks, n = x.shape
+                y = torch.empty(bs, 2, n, dtype=torch.float32, device=dev)
+                check(lib.dasp_bus_fwd(ptr(x), ptr(p), ptr(y), bs, tracks, n, st), "dasp_bus_fwd")
+        ctx.save_for_backward(x, p)
+        ctx.kind = kind
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lib = _abi.lib()
+        x, p = ctx.saved_tensors
+        dev = x.device
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        gp = torch.empty_like(p)
+        with torch.cuda.device(dev):
+            st = stream_ptr(dev)
+            if ctx.kind == "widener":
+                bs, _, n = x.shape
+                nws = lib.dasp_stereo_bwd_workspace_floats(bs, n)
+                ws = _ws(nws, dev)
+                check(lib.dasp_widener_bwd(ptr(gy), ptr(x), ptr(p), ptr(gx), ptr(gp), ptr(ws), nws, bs, n, st),
+                      "dasp_widener_bwd")
+            elif ctx.kind == "panner":
+                bs, tracks, n = x.shape
+                nws = lib.dasp_stereo_bwd_workspace_floats(bs * tracks, n)
+                ws = _ws(nws, dev)
+                check(lib.dasp_panner_bwd(ptr(gy), ptr(x), ptr(p), ptr(gx), ptr(gp), ptr(ws), nws, bs, tracks, n, st),
+                      "dasp_panner_bwd")
+            else:
+                bs, _, tracks, n = x.shape
+                nws = lib.dasp_stereo_bwd_workspace_floats(bs * 2 * tracks, n)
+                ws = _ws(nws, dev)
+                check(lib.dasp_bus_bwd(ptr(gy), ptr(x), ptr(p), ptr(gx), ptr(gp), ptr(ws), nws, bs, tracks, n, st),
+                      "dasp_bus_bwd")
+        return gx, gp, None
+
+
+def _audio_nd(x, ndim, name="x"):
+    if not torch.is_tensor(x) or x.dim() != ndim:
+        raise ValueError(f"{name} must be a {ndim}-dimensional tensor")
+    if not x.is_cuda:
+        raise DaspError(f"{name} is on {x.device}: dasp_pytorch_b200 only runs on CUDA (B200) tensors and has no CPU path")
+    if not x.is_floating_point():
+        raise DaspError(f"{name} must be a floating-point tensor, got {x.dtype}")
+    return x.to(torch.float32).contiguous(), x.dtype
+
+
+def stereo_widener(x: torch.Tensor, sample_rate: float, width: torch.Tensor):
+    """Mid/side stereo widener (reference ``functional.py:580-604``).
+
+    ``x`` is ``(bs, 2, seq_len)``, ``width`` holds ``bs`` elements (0 = mono sum, 0.5 = unchanged,
+    1 = side only).  mid = (L+R)/sqrt2 scaled by 2(1-width), side = (L-R)/sqrt2 scaled by 2 width.
+    """
+    xf, dt = _audio_nd(x, 3)
+    bs, chs, _ = xf.shape
+    assert chs == 2, "Input tensor must have shape (bs, 2, seq_len)"
+    w = _param(width, bs, xf, "width").contiguous()
+    return _StereoFn.apply(xf, w, "widener").to(dt)
+
+
+def stereo_panner(x: torch.Tensor, sample_rate: float, pan: torch.Tensor):
+    """Pan mono tracks across the stereo field (reference ``functional.py:607-636``).
+
+    ``x`` is ``(bs, num_tracks, seq_len)``, ``pan`` in ``[0, 1]`` holds ``bs*num_tracks`` elements; returns
+    ``(bs, 2, num_tracks, seq_len)`` -- the layout the reference's code produces (its docstring says
+    ``(bs, num_tracks, 2, seq_len)``, its ``unsqueeze(1).repeat(1, 2, 1, 1)`` does not).
+    """
+    xf, dt = _audio_nd(x, 3)
+    bs, tracks, _ = xf.shape
+    pn = _param(pan, bs * tracks, xf, "pan").contiguous()
+    return _StereoFn.apply(xf, pn, "panner").to(dt)
+
+
+def stereo_bus(x: torch.Tensor, sample_rate: int, send_db: torch.Tensor):
+    """Sum stereo tracks to a stereo bus with per-track send levels in dB (reference ``functional.py:32-62``).
+
+    ``x`` is ``(bs, 2, tracks, seq_len)``, ``send_db`` holds ``bs*tracks`` elements; returns ``(bs, 2, seq_len)``.
+    """
+    xf, dt = _audio_nd(x, 4)
+    bs, chs, tracks, _ = xf.shape
+    assert chs == 2, "Input tensor must have shape (bs, 2, tracks, seq_len)"
+    sd = _param(send_db, bs * tracks, xf, "send_db").contiguous()
+    return _StereoFn.apply(xf, sd, "bus").to(dt)
 
 
 # --------------------------------------------------------------------------------------

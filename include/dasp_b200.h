@@ -58,6 +58,22 @@ int dasp_distortion_bwd(const float* gy, const float* x, const float* drive_db, 
 /* floats of scratch the two *_bwd calls above need (rows = bs for gain with n = chs*N) */
 int64_t dasp_pointwise_bwd_workspace_floats(int64_t rows, int64_t n);
 
+/* ---- stereo_widener / stereo_panner / stereo_bus      (reference functional.py:580-604, 607-636, 32-62) --
+ * widener: x, y (bs, 2, n), width [bs].   panner: x (bs, tracks, n), pan [bs*tracks], y (bs, 2, tracks, n).
+ * bus: x (bs, 2, tracks, n), send_db [bs*tracks], y (bs, 2, n).
+ * ws: dasp_stereo_bwd_workspace_floats(rows, n) floats with rows = bs (widener), bs*tracks (panner),
+ * bs*2*tracks (bus). */
+int64_t dasp_stereo_bwd_workspace_floats(int64_t rows, int64_t n);
+int dasp_widener_fwd(const float* x, const float* width, float* y, int64_t bs, int64_t n, void* stream);
+int dasp_widener_bwd(const float* gy, const float* x, const float* width, float* gx, float* g_width, float* ws,
+                     int64_t ws_floats, int64_t bs, int64_t n, void* stream);
+int dasp_panner_fwd(const float* x, const float* pan, float* y, int64_t bs, int64_t tracks, int64_t n, void* stream);
+int dasp_panner_bwd(const float* gy, const float* x, const float* pan, float* gx, float* g_pan, float* ws,
+                    int64_t ws_floats, int64_t bs, int64_t tracks, int64_t n, void* stream);
+int dasp_bus_fwd(const float* x, const float* send_db, float* y, int64_t bs, int64_t tracks, int64_t n, void* stream);
+int dasp_bus_bwd(const float* gy, const float* x, const float* send_db, float* gx, float* g_send_db, float* ws,
+                 int64_t ws_floats, int64_t bs, int64_t tracks, int64_t n, void* stream);
+
 /* ---- compressor / expander            (reference functional.py:275-399; :402-403 stub) --
  * kind: 0 = compressor (reference semantics: attack-only smoothing, release_ms unused),
  *       1 = downward expander (new op, same signature; the reference only stubs it).

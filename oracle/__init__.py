@@ -9,6 +9,9 @@ baseline), never as a compute path of ``dasp_pytorch_b200``.
 from oracle.dasp_oracle import (  # noqa: F401
     gain,
     distortion,
+    stereo_widener,
+    stereo_panner,
+    stereo_bus,
     biquad_section,
     eq_sections,
     sos_frequency_sampling,

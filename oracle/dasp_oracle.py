@@ -58,6 +58,43 @@ def distortion(x: torch.Tensor, sample_rate, drive_db: torch.Tensor) -> torch.Te
 
 
 # --------------------------------------------------------------------------------------
+# stereo mixing processors
+# --------------------------------------------------------------------------------------
+
+
+def stereo_widener(x: torch.Tensor, sample_rate, width: torch.Tensor) -> torch.Tensor:
+    """Mid/side widener (functional.py:580-604), restated without the in-place ops.
+
+    mid=(L+R)/sqrt2 * 2(1-w), side=(L-R)/sqrt2 * 2w, left=(mid+side)/sqrt2, right=(mid-side)/sqrt2.
+    ``width`` is reshaped to ``(bs, 1)`` (the reference's broadcast only works for that shape).
+    """
+    bs = x.shape[0]
+    w = width.reshape(bs, 1)
+    r2 = math.sqrt(2.0)
+    mid = (x[:, 0] + x[:, 1]) / r2 * (2.0 * (1.0 - w))
+    side = (x[:, 0] - x[:, 1]) / r2 * (2.0 * w)
+    return torch.stack(((mid + side) / r2, (mid - side) / r2), dim=-2)
+
+
+def stereo_panner(x: torch.Tensor, sample_rate, pan: torch.Tensor) -> torch.Tensor:
+    """Constant-power-ish panner (functional.py:607-636): returns (bs, 2, tracks, N)."""
+    bs, tracks, _ = x.shape
+    theta = pan.reshape(bs, tracks) * (math.pi / 2)
+    lg = torch.sqrt(((math.pi / 2) - theta) * (2 / math.pi) * torch.cos(theta))
+    rg = torch.sqrt(theta * (2 / math.pi) * torch.sin(theta))
+    gains = torch.stack((lg, rg), dim=1).unsqueeze(-1)          # (bs, 2, tracks, 1)
+    return x.unsqueeze(1) * gains
+
+
+def stereo_bus(x: torch.Tensor, sample_rate, send_db: torch.Tensor) -> torch.Tensor:
+    """Stereo bus (functional.py:32-62): (bs, 2, tracks, N) x sends in dB -> (bs, 2, N)."""
+    bs, chs, tracks, _ = x.shape
+    assert chs == 2
+    s = torch.pow(10.0, send_db.reshape(bs, 1, tracks, 1) / 20.0)
+    return (x * s).sum(dim=2)
+
+
+# --------------------------------------------------------------------------------------
 # biquad design + parametric EQ
 # --------------------------------------------------------------------------------------
 

@@ -157,6 +157,32 @@ def main():
     st["filterbank"] = fb.squeeze(1).numpy()
     np.savez_compressed(os.path.join(OUT, "reverb.npz"), **st)
 
+    # ---------------- stereo widener / panner / bus ----------------
+    g = torch.Generator().manual_seed(55)
+    st = {}
+    x = torch.rand(3, 2, 700, generator=g) * 2 - 1
+    w = torch.rand(3, 1, generator=g)
+    st["wid_x"], st["wid_w"] = x.numpy(), w.numpy()
+    f = lambda xx, width: RF.stereo_widener(xx.clone(), sr, width)
+    y32, _, _ = run_with_grads(f, x, {"width": w}, torch.float32)
+    y64, dx, gr = run_with_grads(f, x, {"width": w}, torch.float64)
+    pack("wid", y32, y64, dx, gr, st)
+    x = torch.rand(3, 4, 500, generator=g) * 2 - 1
+    pn = torch.rand(3, 4, generator=g) * 0.9 + 0.05
+    st["pan_x"], st["pan_p"] = x.numpy(), pn.numpy()
+    f = lambda xx, pan: RF.stereo_panner(xx, sr, pan)
+    y32, _, _ = run_with_grads(f, x, {"pan": pn}, torch.float32)
+    y64, dx, gr = run_with_grads(f, x, {"pan": pn}, torch.float64)
+    pack("pan", y32, y64, dx, gr, st)
+    x = torch.rand(3, 2, 5, 400, generator=g) * 2 - 1
+    sd = torch.rand(3, 5, 1, generator=g) * 24 - 18
+    st["bus_x"], st["bus_s"] = x.numpy(), sd.numpy()
+    f = lambda xx, send_db: RF.stereo_bus(xx, sr, send_db)
+    y32, _, _ = run_with_grads(f, x, {"send_db": sd}, torch.float32)
+    y64, dx, gr = run_with_grads(f, x, {"send_db": sd}, torch.float64)
+    pack("bus", y32, y64, dx, gr, st)
+    np.savez_compressed(os.path.join(OUT, "stereo.npz"), **st)
+
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
 
