@@ -353,6 +353,16 @@ def _dynamics(kind, x, sample_rate, threshold_db, ratio, attack_ms, release_ms, 
     return y.to(dt)
 
 
+def dynamics_packed(kind: int, x: torch.Tensor, sample_rate: float, params: torch.Tensor, eps: float = 1e-8,
+                    lookahead_samples: int = 0):
+    """compressor (kind 0) / expander (kind 1) with the six parameters stacked as ``(bs, 6)`` in signature order
+    (threshold, ratio, attack, release, knee, makeup).  One transpose instead of six column copies."""
+    xf, dt = _audio(x)
+    pt = _packed(params, xf.shape[0], 6, xf, "params").t().contiguous()        # (6, bs): rows are contiguous
+    y = _DynamicsFn.apply(xf, pt[0], pt[1], pt[2], pt[4], pt[5], kind, sample_rate, eps, int(lookahead_samples))
+    return y.to(dt)
+
+
 def compressor(
     x: torch.Tensor,
     sample_rate: float,
@@ -493,6 +503,22 @@ def parametric_eq(
     return y.to(dt)
 
 
+def _packed(params, bs: int, ncol: int, like: torch.Tensor, name: str) -> torch.Tensor:
+    if not torch.is_tensor(params) or params.dim() != 2 or tuple(params.shape) != (bs, ncol):
+        raise ValueError(f"{name}: expected a ({bs}, {ncol}) parameter tensor, got {tuple(getattr(params, 'shape', ()))}")
+    if params.device != like.device:
+        raise DaspError(f"{name} is on {params.device} but x is on {like.device}")
+    return params.to(torch.float32).contiguous()
+
+
+def parametric_eq_packed(x: torch.Tensor, sample_rate: float, params: torch.Tensor):
+    """``parametric_eq`` with its 18 parameters already stacked as ``(bs, 18)`` in signature order (physical
+    units).  Used by ``modules.ParametricEQ.process_normalized`` so that the whole normalised-parameter path is
+    one affine kernel + the EQ kernels; gradients flow to ``params``."""
+    xf, dt = _audio(x)
+    return _ParametricEqFn.apply(xf, _packed(params, xf.shape[0], 18, xf, "params"), sample_rate).to(dt)
+
+
 # --------------------------------------------------------------------------------------
 # noise-shaped reverberation
 # --------------------------------------------------------------------------------------
@@ -622,4 +648,24 @@ def noise_shaped_reverberation(
         seed = int(torch.empty((), dtype=torch.int64).random_().item())
     y = _ReverbFn.apply(xf, packed, noise, seed, sample_rate, int(num_samples), int(num_bandpass_taps),
                         REVERB_CHUNK_ITEMS)
+    return y.to(dt)
+
+
+def noise_shaped_reverberation_packed(x: torch.Tensor, sample_rate: float, params: torch.Tensor, num_samples: int = 65536,
+                                      num_bandpass_taps: int = 1023, *, noise: Optional[torch.Tensor] = None):
+    """``noise_shaped_reverberation`` with its 25 parameters stacked as ``(bs, 25)`` (12 gains, 12 decays, mix)."""
+    assert num_bandpass_taps % 2 == 1, "num_bandpass_taps must be odd"
+    xf, dt = _audio(x)
+    bs, chs, _ = xf.shape
+    assert chs <= 2, "only mono/stereo signals are supported"
+    packed = _packed(params, bs, 25, xf, "params")
+    seed = 0
+    if noise is not None:
+        expect = (bs * 2, 12, num_samples + num_bandpass_taps - 1)
+        if tuple(noise.shape) != expect:
+            raise ValueError(f"noise must have shape {expect}, got {tuple(noise.shape)}")
+        noise = noise.to(device=xf.device, dtype=torch.float32).contiguous()
+    else:
+        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    y = _ReverbFn.apply(xf, packed, noise, seed, sample_rate, int(num_samples), int(num_bandpass_taps), REVERB_CHUNK_ITEMS)
     return y.to(dt)

@@ -20,6 +20,7 @@ from typing import Dict
 
 import torch
 
+from dasp_pytorch_b200 import functional as _F
 from dasp_pytorch_b200.functional import (
     compressor,
     distortion,
@@ -49,11 +50,40 @@ class Processor:
     def num_params(self) -> int:
         return len(self.param_ranges)
 
+    # subclasses with a packed kernel entry point set this to (callable(x, sr, packed), the process_fn it mirrors)
+    _packed_path = None
+
     def process_normalized(self, x: torch.Tensor, param_tensor: torch.Tensor):
-        """Run the processor with parameters normalised to (0, 1), shape ``(batch, num_params)``."""
+        """Run the processor with parameters normalised to (0, 1), shape ``(batch, num_params)``.
+
+        Fast path: when ``process_fn`` is still this package's kernel entry, the whole
+        parameter handling is ONE range-check reduction and ONE affine kernel on the packed ``(batch, P)``
+        tensor, which then goes to the kernels as is -- instead of the reference's per-parameter slicing,
+        2 host syncs and ~3 tiny kernels per parameter (modules.py:56-91).  Same errors, same results.
+        """
+        if self._packed_path is not None and self.process_fn is self._packed_path[1] and param_tensor.is_cuda:
+            if param_tensor.dim() != 2 or param_tensor.shape[1] != len(self.param_ranges):
+                raise ValueError(
+                    f"Parameter tensor has {param_tensor.shape[1] if param_tensor.dim() == 2 else '?'} parameters, "
+                    f"but processor has {len(self.param_ranges)} parameters."
+                )
+            if not self._range_check(param_tensor):
+                self.denormalize_param_dict(self.extract_param_dict(param_tensor))      # raises with the name
+            scale, offset = self._affine(param_tensor.device)
+            return self._packed_path[0](x, self.sample_rate, torch.addcmul(offset, param_tensor.to(torch.float32), scale))
         param_dict = self.extract_param_dict(param_tensor)
         denorm = self.denormalize_param_dict(param_dict, _checked=self._range_check(param_tensor))
         return self.process_fn(x, self.sample_rate, **denorm)
+
+    def _affine(self, device):
+        key = (str(device), tuple(self.param_ranges.values()))
+        cache = self.__dict__.setdefault("_affine_cache", {})
+        if key not in cache:
+            lo = torch.tensor([r[0] for r in self.param_ranges.values()], dtype=torch.float32)
+            hi = torch.tensor([r[1] for r in self.param_ranges.values()], dtype=torch.float32)
+            cache.clear()
+            cache[key] = ((hi - lo).to(device), lo.to(device))
+        return cache[key]
 
     def process(self, x: torch.Tensor, *args):
         return self.process_fn(x, *args)
@@ -107,6 +137,7 @@ class ParametricEQ(Processor):
                  min_q_factor: float = 0.1, max_q_factor: float = 6.0):
         self.sample_rate = sample_rate
         self.process_fn = parametric_eq
+        self._packed_path = (_F.parametric_eq_packed, parametric_eq)
         g, q = (min_gain_db, max_gain_db), (min_q_factor, max_q_factor)
         top = (sample_rate // 2) - 1000
         cut = {"low_shelf": (20, 2000), "band0": (80, 2000), "band1": (2000, 8000), "band2": (8000, 12000),
@@ -139,6 +170,7 @@ class Compressor(_Dynamics):
     def __init__(self, sample_rate: int, **kw):
         super().__init__(sample_rate, **kw)
         self.process_fn = compressor
+        self._packed_path = (lambda x, sr, p: _F.dynamics_packed(0, x, sr, p), compressor)
 
 
 class Expander(_Dynamics):
@@ -147,6 +179,7 @@ class Expander(_Dynamics):
     def __init__(self, sample_rate: int, max_ratio: float = 4.0, **kw):
         super().__init__(sample_rate, max_ratio=max_ratio, **kw)
         self.process_fn = expander
+        self._packed_path = (lambda x, sr, p: _F.dynamics_packed(1, x, sr, p), expander)
 
 
 class NoiseShapedReverb(Processor):
@@ -155,6 +188,7 @@ class NoiseShapedReverb(Processor):
                  max_mix: float = 1.0):
         self.sample_rate = sample_rate
         self.process_fn = noise_shaped_reverberation
+        self._packed_path = (_F.noise_shaped_reverberation_packed, noise_shaped_reverberation)
         self.param_ranges = {f"band{i}_gain": (min_band_gain, max_band_gain) for i in range(12)}
         self.param_ranges.update({f"band{i}_decay": (min_band_decay, max_band_decay) for i in range(12)})
         self.param_ranges["mix"] = (min_mix, max_mix)
