@@ -78,17 +78,27 @@ struct PoleTables {
 };
 
 __device__ __forceinline__ void make_tables(PoleTables& t, float attack_ms, float sample_rate, int lane) {
-  // alpha = exp(-ln9 / (sr * attack_ms / 1e3))  (functional.py:339-342), evaluated in fp64
+  // alpha = exp(-ln9 / (sr * attack_ms / 1e3))  (functional.py:339-342), evaluated in fp64; every power is
+  // then built from it by fp64 multiplications (one exp2 call instead of fifteen)
   const double l2a = -3.169925001442312 /* log2(9) */ / ((double)sample_rate * ((double)attack_ms * 1e-3));
   const double a = exp2(l2a);
   t.alpha = (float)a;
   t.beta = (float)(1.0 - a);
+  double pw = a;
 #pragma unroll
-  for (int j = 0; j <= kE; ++j) t.apow[j] = (float)exp2(l2a * (double)(j + 1));
+  for (int j = 0; j <= kE; ++j) { t.apow[j] = (float)pw; pw *= a; }      // a^1 .. a^(E+1)
+  double st = 1.0;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) t.step[k] = (float)exp2(l2a * (double)(kE << k));
-  t.lane_pow = (float)exp2(l2a * (double)(kE * lane));
-  t.warp_pow = (float)exp2(l2a * (double)(kE * 32));
+  for (int j = 0; j < kE; ++j) st *= a;                                   // a^E
+  double lp = 1.0;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    t.step[k] = (float)st;
+    if ((lane >> k) & 1) lp *= st;                                        // a^(E*lane) from the bits of lane
+    st *= st;
+  }
+  t.lane_pow = (float)lp;
+  t.warp_pow = (float)st;                                                 // a^(32E)
 }
 
 // Forward-in-time scan of first-order states across the CTA.
@@ -158,48 +168,66 @@ __device__ __forceinline__ float scan_reverse(float v, float& c_tile, const Pole
 // ---- static gain computer (dB in, dB gain out) + partial derivatives ----------------------
 struct CurveOut { float gc, d_xdb, d_t, d_r, d_w; };
 
+// per-item constants of the static curve: every division is done once per item, not once per sample
+struct CurveK {
+  float T, half, lo, hi;       // threshold, W/2, knee edges T -+ W/2
+  float slope;                 // compressor: 1/R - 1          expander: 1 - R
+  float inv_w, inv_2w;         // 1/W, 1/(2W)  (W == 0 -> inf, poisoning the knee exactly like the reference's 0/0)
+  float inv_r2;                // 1/R^2
+  float r_m1;                  // R - 1
+};
+__device__ __forceinline__ CurveK make_curve(Curve cv, float T, float R, float Wk) {
+  CurveK k;
+  k.T = T; k.half = 0.5f * Wk; k.lo = T - k.half; k.hi = T + k.half;
+  k.slope = (cv == Curve::Compress) ? (1.0f / R - 1.0f) : (1.0f - R);
+  k.inv_w = 1.0f / Wk; k.inv_2w = 0.5f * k.inv_w;
+  k.inv_r2 = 1.0f / (R * R);
+  k.r_m1 = R - 1.0f;
+  return k;
+}
+
 template <Curve CV, bool GRAD>
-__device__ __forceinline__ CurveOut gain_computer(float xdb, float T, float R, float Wk) {
+__device__ __forceinline__ CurveOut gain_computer(float xdb, const CurveK& k) {
   CurveOut o; o.gc = 0.f; o.d_xdb = 0.f; o.d_t = 0.f; o.d_r = 0.f; o.d_w = 0.f;
-  const float half = 0.5f * Wk;
-  const bool in_knee = (xdb >= T - half) && (xdb <= T + half);
+  const bool in_knee = (xdb >= k.lo) && (xdb <= k.hi);
   if (CV == Curve::Compress) {
     // functional.py:350-369 expressed as gc = x_sc - x_db
-    const float slope = 1.0f / R - 1.0f;
     if (in_knee) {
-      const float d = xdb - T + half;
-      o.gc = slope * d * d / (2.0f * Wk);
+      const float d = xdb - k.lo;                     // x_db - T + W/2
+      const float q = d * d * k.inv_2w;               // d^2 / (2W)
+      o.gc = k.slope * q;
       if (GRAD) {
-        o.d_xdb = slope * d / Wk;
+        o.d_xdb = k.slope * d * k.inv_w;
         o.d_t = -o.d_xdb;
-        o.d_r = -d * d / (2.0f * Wk * R * R);
-        o.d_w = slope * (d / (2.0f * Wk) - d * d / (2.0f * Wk * Wk));
+        o.d_r = -q * k.inv_r2;
+        o.d_w = k.slope * (d * k.inv_2w - q * k.inv_w);
       }
-    } else if (xdb > T + half) {
-      o.gc = (T - xdb) * (1.0f - 1.0f / R);
+    } else if (xdb > k.hi) {
+      o.gc = (xdb - k.T) * k.slope;                   // (T - x)(1 - 1/R)
       if (GRAD) {
-        o.d_xdb = slope;
-        o.d_t = -slope;
-        o.d_r = (T - xdb) / (R * R);
+        o.d_xdb = k.slope;
+        o.d_t = -k.slope;
+        o.d_r = (k.T - xdb) * k.inv_r2;
       }
     }
   } else {
     // downward expander (oracle/dasp_oracle.py::_expander_curve)
     if (in_knee) {
-      const float d = xdb - T - half;
-      o.gc = (1.0f - R) * d * d / (2.0f * Wk);
+      const float d = xdb - k.hi;                     // x_db - T - W/2
+      const float q = d * d * k.inv_2w;
+      o.gc = k.slope * q;                             // (1 - R) d^2 / (2W)
       if (GRAD) {
-        o.d_xdb = (1.0f - R) * d / Wk;
+        o.d_xdb = k.slope * d * k.inv_w;
         o.d_t = -o.d_xdb;
-        o.d_r = -d * d / (2.0f * Wk);
-        o.d_w = (1.0f - R) * (-d / (2.0f * Wk) - d * d / (2.0f * Wk * Wk));
+        o.d_r = -q;
+        o.d_w = k.slope * (-d * k.inv_2w - q * k.inv_w);
       }
-    } else if (xdb < T - half) {
-      o.gc = (R - 1.0f) * (xdb - T);
+    } else if (xdb < k.lo) {
+      o.gc = k.r_m1 * (xdb - k.T);
       if (GRAD) {
-        o.d_xdb = R - 1.0f;
-        o.d_t = -(R - 1.0f);
-        o.d_r = xdb - T;
+        o.d_xdb = k.r_m1;
+        o.d_t = -k.r_m1;
+        o.d_r = xdb - k.T;
       }
     }
   }
@@ -223,7 +251,7 @@ struct Smem {
 constexpr size_t kSmemHeader = 256;
 
 // =============================================================================== forward
-template <Curve CV, int W>
+template <Curve CV, int W, bool LA>     // LA: lookahead_samples > 0 (rare; kept out of the common instantiation)
 __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<W> sm(smem_raw);
@@ -232,7 +260,8 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
   const int C = p.chs;
   const int tile_len = W * 32 * kE;
 
-  const float T = p.threshold_db[item], R = p.ratio[item], Wk = p.knee_db[item], M = p.makeup_db[item];
+  const float M = p.makeup_db[item];
+  const CurveK ck = make_curve(CV, p.threshold_db[item], p.ratio[item], p.knee_db[item]);
   PoleTables tb;
   make_tables(tb, p.attack_ms[item], p.sample_rate, lane);
 
@@ -265,7 +294,7 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
 #pragma unroll
       for (int j = 0; j < kE; ++j) {
         float gc = 0.f;
-        if (n0 + j < p.n) gc = gain_computer<CV, false>(level_db(xs[j], p.eps), T, R, Wk).gc;
+        if (n0 + j < p.n) gc = gain_computer<CV, false>(level_db(xs[j], p.eps), ck).gc;
         run = fmaf(tb.alpha, run, tb.beta * gc);
         s[j] = run;
       }
@@ -276,7 +305,7 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
     float G[kE];
 #pragma unroll
     for (int j = 0; j < kE; ++j) G[j] = exp2f((fmaf(tb.apow[j], c_in, s[j]) + M) * kLog2Of10Over20);
-    if (p.lookahead == 0) {
+    if (!LA) {
       for (int c = 0; c < C; ++c) {
         float* xb = pipe.buf(st, c) + off;
 #pragma unroll
@@ -300,7 +329,7 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
 }
 
 // =============================================================================== backward
-template <Curve CV, int W>
+template <Curve CV, int W, bool LA>
 __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<W> sm(smem_raw);
@@ -311,15 +340,15 @@ __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
   const int tile_len = W * 32 * kE;
   const int la = p.lookahead;
 
-  const float T = p.threshold_db[item], R = p.ratio[item], Wk = p.knee_db[item], M = p.makeup_db[item];
+  const float M = p.makeup_db[item];
+  const CurveK ck = make_curve(CV, p.threshold_db[item], p.ratio[item], p.knee_db[item]);
   const float attack = p.attack_ms[item];
   PoleTables tb;
   make_tables(tb, attack, p.sample_rate, lane);
-  float rlane_pow;
-  {
-    const double l2a = -3.169925001442312 / ((double)p.sample_rate * ((double)attack * 1e-3));
-    rlane_pow = (float)exp2(l2a * (double)(kE * (31 - lane)));
-  }
+  // a^(E*(31-lane)): the same construction seen from the other end of the warp
+  PoleTables tr;
+  make_tables(tr, attack, p.sample_rate, 31 - lane);
+  const float rlane_pow = tr.lane_pow;
 
   TileGeom g{p.n, tile_len, p.ntiles, true};
   const int64_t base = (int64_t)item * C * p.n;
@@ -351,7 +380,7 @@ __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
 #pragma unroll
       for (int j = 0; j < kE; ++j) {
         CurveOut o; o.gc = 0.f; o.d_xdb = 0.f; o.d_t = 0.f; o.d_r = 0.f; o.d_w = 0.f;
-        if (n0 + j < p.n) o = gain_computer<CV, true>(level_db(xs[j], p.eps), T, R, Wk);
+        if (n0 + j < p.n) o = gain_computer<CV, true>(level_db(xs[j], p.eps), ck);
         gcv[j] = o.gc; dxdbv[j] = o.d_xdb; drv[j] = o.d_r; dwv[j] = o.d_w;
         run = fmaf(tb.alpha, run, tb.beta * o.gc);
         s[j] = run;
@@ -371,7 +400,7 @@ __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
       for (int c = 0; c < C; ++c) {
         const float* xb = pipe.buf(st, c) + off;
         const float* gb = pipe.buf(st, C + c) + off;
-        if (la == 0) {
+        if (!LA) {
 #pragma unroll
           for (int j = 0; j < kE; ++j) dG[j] = fmaf(gb[j], xb[j], dG[j]);
         } else {
@@ -411,11 +440,11 @@ __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
         acc_t = fmaf(dgc, -dxdbv[j], acc_t);
         acc_r = fmaf(dgc, drv[j], acc_r);
         acc_w = fmaf(dgc, dwv[j], acc_w);
-        if (fabsf(xs[j]) >= p.eps) dx = dgc * dxdbv[j] * kDbGradScale / xs[j];
+        if (fabsf(xs[j]) >= p.eps) dx = __fdividef(dgc * dxdbv[j] * kDbGradScale, xs[j]);
       }
       dxs[j] = dx;
     }
-    if (la == 0) {
+    if (!LA) {
       for (int c = 0; c < C; ++c) {
         float* gb = pipe.buf(st, C + c) + off;
 #pragma unroll
@@ -487,21 +516,29 @@ int pick_warps(int64_t bs, int chs, int nbuf_per_ch) {
 }
 size_t smem_bytes(int w, int nbuf) { return kSmemHeader + (size_t)kStages * nbuf * (w * 32 * kE) * 4; }
 
-template <Curve CV, int W>
-int launch_fwd_w(const DynParams& p, int64_t bs, cudaStream_t st) {
+template <Curve CV, int W, bool LA>
+int launch_fwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
   const size_t smem = smem_bytes(W, p.chs);
-  DASP_CUDA_OK(cudaFuncSetAttribute(dynamics_fwd_kernel<CV, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dynamics_fwd_kernel<CV, W><<<(unsigned)bs, W * 32, smem, st>>>(p);
+  DASP_CUDA_OK(cudaFuncSetAttribute(dynamics_fwd_kernel<CV, W, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dynamics_fwd_kernel<CV, W, LA><<<(unsigned)bs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("dynamics_fwd_kernel");
   return DASP_OK;
 }
-template <Curve CV, int W>
-int launch_bwd_w(const DynParams& p, int64_t bs, cudaStream_t st) {
+template <Curve CV, int W, bool LA>
+int launch_bwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
   const size_t smem = smem_bytes(W, 2 * p.chs);
-  DASP_CUDA_OK(cudaFuncSetAttribute(dynamics_bwd_kernel<CV, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dynamics_bwd_kernel<CV, W><<<(unsigned)bs, W * 32, smem, st>>>(p);
+  DASP_CUDA_OK(cudaFuncSetAttribute(dynamics_bwd_kernel<CV, W, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dynamics_bwd_kernel<CV, W, LA><<<(unsigned)bs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("dynamics_bwd_kernel");
   return DASP_OK;
+}
+template <Curve CV, int W>
+int launch_fwd_w(const DynParams& p, int64_t bs, cudaStream_t st) {
+  return p.lookahead > 0 ? launch_fwd_la<CV, W, true>(p, bs, st) : launch_fwd_la<CV, W, false>(p, bs, st);
+}
+template <Curve CV, int W>
+int launch_bwd_w(const DynParams& p, int64_t bs, cudaStream_t st) {
+  return p.lookahead > 0 ? launch_bwd_la<CV, W, true>(p, bs, st) : launch_bwd_la<CV, W, false>(p, bs, st);
 }
 
 template <Curve CV>
