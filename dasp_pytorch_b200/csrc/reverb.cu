@@ -5,28 +5,25 @@
 // white-noise signals (1023-tap FIRs, time-domain conv1d, functional.py:551-556), each shaped by an
 // exponential envelope and a gain (:561-567), then convolves the audio with it by a second
 // time-domain conv1d with an L-tap kernel (:570-572).  >99.9 % of its time is those two direct
-// convolutions.  Here both are FFT convolutions, batched through cuFFT,
-// with everything between the transforms fused into four streaming kernels:
+// convolutions.  Here both are FFT convolutions built from ONE transform shape,
+// the 8192-point batched C2C that cuFFT runs as a single shared-memory kernel (~4.5 TB/s effective on
+// B200; its long transforms reach 0.3-1.5 TB/s), with everything between the transforms fused:
 //
-//   Only the first Leff = min(L, N) taps of the impulse response can reach the N output samples
-//   (y[n] = sum_{t<=n} IR[t] x[n-t], n < N), so only those are synthesised -- an exact saving (the
-//   reference computes the rest and then multiplies it by the zero padding).
-//   IR synthesis (12 bands x 2 channels per item):
-//     noise (user tensor in parity mode, Philox4x32-10 on device otherwise) written as overlap-save
-//     blocks of nb samples, the LEFT and RIGHT channel of a band packed as real/imag of one complex
-//     sequence (both channels see the same real filter, so one complex FFT filters both)  ->
-//     batched in-place C2C (single-kernel shared-memory cuFFT path)  ->  fused multiply by the cached
-//     band spectrum H_k/nb  ->  batched inverse C2C (its output, the filtered noise f, is kept for the
-//     backward)  ->  fused envelope * gain * band-mean kernel writing both channels of the IR straight
-//     into the zero-padded input buffer of the next FFT.
-//   apply: R2C(x), R2C(IR) at n2 >= N+Leff-1, fused complex multiply, C2R, fused crop + wet/dry mix.
-//     The two spectra are kept for the backward.
-//   Items are processed in chunks of a few items so the transient buffers (noise, block spectra)
-//   stay inside the 126 MB L2 instead of round-tripping through HBM between the passes.
+//   * Only the first Leff = min(L, N) taps of the impulse response can reach the N output samples
+//     (y[n] = sum_{t<=n} IR[t] x[n-t], n < N), so only those are synthesised -- an exact saving.
+//   * The LEFT and RIGHT channel of a band / of the audio are packed as real/imag of one complex sequence.
+//   * IR synthesis, device noise (default): spectral_gen_kernel draws the FILTERED noise spectrum directly
+//     (Philox4x32-10 + Box-Muller; see the comment at the kernel), one inverse C2C, shape_ir_pp_kernel
+//     (envelope * gain * band mean -> IR written straight into the partition layout of the convolution).
+//   * IR synthesis, parity mode (caller's noise tensor): overlap-save blocks -> C2C -> cmul_filter_pairs ->
+//     inverse C2C -> shape_ir_pairs_kernel.
+//   * Audio convolution: uniformly partitioned overlap-save in the frequency domain (x_blocks_kernel, C2C,
+//     partition_mac_kernel, inverse C2C, mix_blocks_kernel).
+//   * Items are processed in chunks (128 by default) to bound the workspace.
 //
-// Backward (A.5): one R2C of mix*g, two conjugate multiplies with the saved spectra, two C2R give
-// dL/dx and dL/dIR; the band-parameter gradients are reductions of dL/dIR * env * f over time and
-// channels (deterministic two-stage reduction); dL/dmix = sum g (wet - x).
+// Backward (A.5): g_blocks_kernel (+ dL/dmix partials), C2C, two correlation passes of partition_mac_kernel
+// against the saved block spectra (dL/dx windows, dL/dIR partitions), two inverse C2C, finish_dx_blocks_kernel,
+// ir_grad_*_kernel (dL/dIR * env * f reductions for the 24 band parameters; deterministic two-stage sums).
 #include <cufft.h>
 #include <curand_kernel.h>
 #include <math.h>
@@ -44,7 +41,6 @@ namespace {
 constexpr int kBands = 12;
 constexpr int kB = 4096;          // partition / hop of the audio convolution
 constexpr int kNbA = 2 * kB;      // its FFT length (single-kernel cuFFT C2C size)
-constexpr int kSig = 2 * kBands;     // band signals per item (stereo)
 constexpr double kPi = 3.14159265358979323846;
 
 #define DASP_CUFFT_OK(expr)                                                        \
@@ -100,28 +96,6 @@ void octave_filterbank(int taps, double sr, std::vector<float>& out) {
 }
 
 // ------------------------------------------------------------------ geometry
-bool is_7smooth(int64_t v) {
-  for (int p : {2, 3, 5, 7})
-    while (v % p == 0) v /= p;
-  return v == 1;
-}
-int64_t next_fast_even(int64_t v) {
-  if (v < 2) v = 2;
-  if (v & 1) ++v;
-  while (!is_7smooth(v)) v += 2;
-  return v;
-}
-
-// FFT length for the audio convolution: 7-smooth and a multiple of a large power of two (measured on
-// B200: 98304 = 2^15*3 runs the C2R 2.3x faster than 96000 = 2^8*3*5^3)
-int64_t next_conv_len(int64_t v) {
-  int64_t step = 2;
-  while (step < 1024 && step * 64 <= v) step *= 2;
-  int64_t c = ((v + step - 1) / step) * step;
-  while (!is_7smooth(c)) c += step;
-  return c;
-}
-
 struct Geom {
   int64_t bs, n, L, taps, P;
   int64_t leff;                 // min(L, n): the only IR taps that can reach the output
@@ -711,14 +685,6 @@ __global__ void reverb_param_grad_kernel(const float* __restrict__ ir_part, cons
     for (int i = 0; i < mix_blocks; ++i) s += (double)mix_part[bl * mix_blocks + i];
   }
   gparams[(item0 + bl) * 25 + q] = (float)s;
-}
-
-inline unsigned grid_for(int64_t total, int threads = 256) {
-  int64_t blocks = (total + threads - 1) / threads;
-  const int64_t cap = (int64_t)sm_count() * 16;
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
-  return (unsigned)blocks;
 }
 
 // device-resident band spectra H_k: 12 x nb complex (full spectrum of the real taps), scaled by 1/nb;
