@@ -137,6 +137,22 @@ def test_reverb_device_noise_band_statistics(cuda_device):
     assert 0.7 < float(dec_new / dec_ref) < 1.4
 
 
+def test_reverb_long_audio_and_long_filters(cuda_device):
+    """examples/demo.py-like length (N >> IR): 49 audio blocks x 16 IR partitions takes the generic
+    (non register-cached) multiply path and a polyphase factor of 9; plus a 4095-tap filter bank (32768-pt blocks)."""
+    import dasp_pytorch_b200 as D
+    g = torch.Generator().manual_seed(12)
+    x = torch.rand(1, 2, 200000, generator=g) * 2 - 1
+    _check(cuda_device, x, _params01(1, 77), 65536, 1023, seed=5)
+    x2 = torch.rand(2, 1, 30000, generator=g) * 2 - 1
+    _check(cuda_device, x2, _params01(2, 78), 20000, 4095, seed=6)
+    # device-noise path on the same geometries: finite, stereo, right shape
+    xs = x.to(cuda_device)
+    p = [q.to(cuda_device) for q in _params01(1, 77)]
+    y = D.noise_shaped_reverberation(xs, SR, *p)                       # reference defaults: 65536 samples, 1023 taps
+    assert y.shape == (1, 2, 200000) and bool(torch.isfinite(y).all())
+
+
 def test_reverb_contract(cuda_device):
     import dasp_pytorch_b200 as D
     x = torch.rand(2, 2, 512, device=cuda_device)
