@@ -268,9 +268,9 @@ def main():
         cols = list(pd.unbind(1))
         return xd, cols[:18], cols[18:24], cols[24:49], dd
 
-    x, eq, comp, rev, drive = to_leaves(x_pin.to(dev), p_pin.to(dev), d_pin.to(dev))
-    p_dev = eq[0]._base if eq[0]._base is not None else None
-    leaves = [x, drive] + ([p_dev] if p_dev is not None else eq + comp + rev)
+    p_dev = p_pin.to(dev)
+    x, eq, comp, rev, drive = to_leaves(x_pin.to(dev), p_dev, d_pin.to(dev))
+    leaves = [x, drive, p_dev]
 
     def step():
         for t in leaves:
