@@ -299,31 +299,39 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
     ga[j2] = a;
     gb[R - 1 - j2] = m;          // mirror of bin j1 + nb j2 is bin (nb - j1) + nb (R-1-j2)
   }
-  float2 root[R];
+  // The two residue classes (j1 and nb - j1) go through the SAME R-point DFT and twiddle ladder, so they are
+  // packed into the two lanes of Blackwell's fp32x2 instructions (FFMA2/FMUL2: one issue slot, two FMAs).
+  float2 gx[R], gy[R];                       // (class A, class B) real parts / imaginary parts
 #pragma unroll
-  for (int m = 0; m < R; ++m) root[m] = c_root[R][m];
+  for (int j2 = 0; j2 < R; ++j2) { gx[j2] = make_float2(ga[j2].x, gb[j2].x); gy[j2] = make_float2(ga[j2].y, gb[j2].y); }
+  float2 rx[R], ry[R], nry[R];               // roots of unity broadcast to both lanes
+#pragma unroll
+  for (int m = 0; m < R; ++m) {
+    const float2 r = c_root[R][m];
+    rx[m] = make_float2(r.x, r.x); ry[m] = make_float2(r.y, r.y); nry[m] = make_float2(-r.y, -r.y);
+  }
   float2 w1a, w1b;
   sincospif(2.0f * (float)j1 / (float)n1, &w1a.y, &w1a.x);
   sincospif(2.0f * (float)(nb - j1) / (float)n1, &w1b.y, &w1b.x);
-  float2 twa = make_float2(1.f, 0.f), twb = make_float2(1.f, 0.f);
+  const float2 wx = make_float2(w1a.x, w1b.x), wy = make_float2(w1a.y, w1b.y), nwy = make_float2(-w1a.y, -w1b.y);
+  float2 tx = make_float2(1.f, 1.f), ty = make_float2(0.f, 0.f);      // twiddle e^{2 pi i j b / n1}, both classes
   float2* outp = C + ((il * kBands + k) * R) * (int64_t)nb;
 #pragma unroll
   for (int b = 0; b < R; ++b) {
-    float2 sa = make_float2(0.f, 0.f), sb = make_float2(0.f, 0.f);
+    float2 sre = make_float2(0.f, 0.f), sim = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j2 = 0; j2 < R; ++j2) {
-      const float2 r = root[(j2 * b) % R];
-      sa.x = fmaf(ga[j2].x, r.x, fmaf(-ga[j2].y, r.y, sa.x));
-      sa.y = fmaf(ga[j2].x, r.y, fmaf(ga[j2].y, r.x, sa.y));
-      sb.x = fmaf(gb[j2].x, r.x, fmaf(-gb[j2].y, r.y, sb.x));
-      sb.y = fmaf(gb[j2].x, r.y, fmaf(gb[j2].y, r.x, sb.y));
+      const int m = (j2 * b) % R;
+      sre = __ffma2_rn(gx[j2], rx[m], __ffma2_rn(gy[j2], nry[m], sre));
+      sim = __ffma2_rn(gx[j2], ry[m], __ffma2_rn(gy[j2], rx[m], sim));
     }
-    outp[(int64_t)b * nb + j1] = make_float2(sa.x * twa.x - sa.y * twa.y, sa.x * twa.y + sa.y * twa.x);
-    if (!self_mirror)
-      outp[(int64_t)b * nb + (nb - j1)] = make_float2(sb.x * twb.x - sb.y * twb.y, sb.x * twb.y + sb.y * twb.x);
-    const float2 na = make_float2(twa.x * w1a.x - twa.y * w1a.y, twa.x * w1a.y + twa.y * w1a.x);
-    const float2 nbw = make_float2(twb.x * w1b.x - twb.y * w1b.y, twb.x * w1b.y + twb.y * w1b.x);
-    twa = na; twb = nbw;
+    const float2 ore = __ffma2_rn(sre, tx, __fmul2_rn(sim, make_float2(-ty.x, -ty.y)));
+    const float2 oim = __ffma2_rn(sre, ty, __fmul2_rn(sim, tx));
+    outp[(int64_t)b * nb + j1] = make_float2(ore.x, oim.x);
+    if (!self_mirror) outp[(int64_t)b * nb + (nb - j1)] = make_float2(ore.y, oim.y);
+    const float2 ntx = __ffma2_rn(tx, wx, __fmul2_rn(ty, nwy));
+    ty = __ffma2_rn(tx, wy, __fmul2_rn(ty, wx));
+    tx = ntx;
   }
 }
 
@@ -409,19 +417,27 @@ __global__ void ir_grad_pp_kernel(const float2* __restrict__ Et, const float2* _
   float s0[kBands], s1[kBands];
 #pragma unroll
   for (int k = 0; k < kBands; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < leff; t += gridDim.x * blockDim.x) {
+  // two time points per iteration: 24 independent 8-byte loads in flight per thread
+  const int stride = gridDim.x * blockDim.x;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < leff; t += 2 * stride) {
+    const int t2 = t + stride;
+    const bool has2 = t2 < leff;
     const int a = t / R, ph = t - a * R;
+    const int a2 = has2 ? t2 / R : a, ph2 = has2 ? t2 - a2 * R : ph;
     const float2 gd = de[(t / kB) * kNbA + (t % kB)];
+    const float2 gd2 = has2 ? de[(t2 / kB) * kNbA + (t2 % kB)] : make_float2(0.f, 0.f);
     const float2* c0 = cb + (int64_t)ph * nb + a;
-    float2 v[kBands];
+    const float2* c1 = cb + (int64_t)ph2 * nb + a2;
+    float2 v[kBands], v2[kBands];
 #pragma unroll
-    for (int k = 0; k < kBands; ++k) v[k] = c0[(int64_t)k * R * nb];
-    const float tt = time_axis(t, L, step);
+    for (int k = 0; k < kBands; ++k) { v[k] = c0[(int64_t)k * R * nb]; v2[k] = c1[(int64_t)k * R * nb]; }
+    const float tt = time_axis(t, L, step), tt2 = time_axis(has2 ? t2 : t, L, step);
 #pragma unroll
     for (int k = 0; k < kBands; ++k) {
       const float w = fmaf(gd.x, v[k].x, gd.y * v[k].y) * __expf(rk[k] * tt);
-      s0[k] += w;
-      s1[k] = fmaf(w, tt, s1[k]);
+      const float w2 = fmaf(gd2.x, v2[k].x, gd2.y * v2[k].y) * __expf(rk[k] * tt2);
+      s0[k] += w + w2;
+      s1[k] = fmaf(w, tt, fmaf(w2, tt2, s1[k]));
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
