@@ -235,14 +235,20 @@ __global__ void cmul_filter_pairs_kernel(float2* __restrict__ C, const float2* _
 // Left/right are packed as G_left + i G_right; one Philox call per canonical bin yields both channels.
 // Philox4x32-10 (Salmon et al., SC'11), counter = (c0, c1, c2, c3), key = (k0, k1); written out instead of the
 // cuRAND state machinery because this kernel needs exactly one block of 4 words per call site
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+struct PhiloxKeys { uint2 k[10]; };           // the ten round keys (key + r * Weyl constants): one schedule per thread
+__device__ __forceinline__ PhiloxKeys philox_keys(unsigned long long seed) {
+  PhiloxKeys ks;
+  uint2 k = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+#pragma unroll
+  for (int r = 0; r < 10; ++r) { ks.k[r] = k; k.x += 0x9E3779B9u; k.y += 0xBB67AE85u; }
+  return ks;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& ks) {
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
     const unsigned long long p0 = (unsigned long long)0xD2511F53u * c.x;
     const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c.z;
-    c = make_uint4((unsigned)(p1 >> 32) ^ c.y ^ k.x, (unsigned)p1, (unsigned)(p0 >> 32) ^ c.w ^ k.y, (unsigned)p0);
-    k.x += 0x9E3779B9u;
-    k.y += 0xBB67AE85u;
+    c = make_uint4((unsigned)(p1 >> 32) ^ c.y ^ ks.k[r].x, (unsigned)p1, (unsigned)(p0 >> 32) ^ c.w ^ ks.k[r].y, (unsigned)p0);
   }
   return c;
 }
@@ -271,13 +277,15 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
   const unsigned long long pair = (unsigned long long)((item0 + il) * kBands + k);
   const float2* h = H1 + (int64_t)k * (n1h + 1);
   const float s_half = sqrtf(0.5f * (float)n1), s_full = sqrtf((float)n1);
+  const PhiloxKeys keys = philox_keys(seed);
 
   // value of the packed spectrum G_left + i G_right at bin j (0 <= j < n1) and at its mirror n1 - j
-  auto draw = [&](int j, float2& at_j, float2& at_mirror) {
-    const int jc = j <= n1h ? j : n1 - j;
+  // `canonical` (j <= n1/2) is a compile-time fact of the unrolled call site: for j1 in [0, nb/2] the bin
+  // j1 + nb j2 lies in the lower half exactly when 2 j2 < R (the only tie, j = n1/2, is its own mirror)
+  auto draw = [&](int j, bool canonical, float2& at_j, float2& at_mirror) {
+    const int jc = canonical ? j : n1 - j;
     // counter = (canonical bin, band pair), key = seed: one Philox block -> both channels' complex Gaussian
-    const uint4 rnd = philox4x32_10(make_uint4((unsigned)jc, (unsigned)pair, (unsigned)(pair >> 32), 0x5eedu),
-                                    make_uint2((unsigned)seed, (unsigned)(seed >> 32)));
+    const uint4 rnd = philox4x32_10(make_uint4((unsigned)jc, (unsigned)pair, (unsigned)(pair >> 32), 0x5eedu), keys);
     const float2 nl = box_muller(rnd.x, rnd.y), nr = box_muller(rnd.z, rnd.w);
     float2 zl, zr;
     if (jc == 0 || jc == n1h) { zl = make_float2(nl.x * s_full, 0.f); zr = make_float2(nr.x * s_full, 0.f); }
@@ -287,7 +295,7 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
     const float2 sr = make_float2(w.x * zr.x - w.y * zr.y, w.x * zr.y + w.y * zr.x);   // H Z_right
     const float2 canon = make_float2(sl.x - sr.y, sl.y + sr.x);      // S_l + i S_r           (bin jc)
     const float2 mirr = make_float2(sl.x + sr.y, sr.x - sl.y);       // conj(S_l) + i conj(S_r) (bin n1 - jc)
-    if (j == jc) { at_j = canon; at_mirror = mirr; } else { at_j = mirr; at_mirror = canon; }
+    if (canonical) { at_j = canon; at_mirror = mirr; } else { at_j = mirr; at_mirror = canon; }
   };
 
   float2 ga[R], gb[R];
@@ -295,7 +303,7 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
 #pragma unroll
   for (int j2 = 0; j2 < R; ++j2) {
     float2 a, m;
-    draw(j1 + nb * j2, a, m);
+    draw(j1 + nb * j2, 2 * j2 < R, a, m);
     ga[j2] = a;
     gb[R - 1 - j2] = m;          // mirror of bin j1 + nb j2 is bin (nb - j1) + nb (R-1-j2)
   }
