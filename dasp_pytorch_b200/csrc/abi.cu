@@ -30,6 +30,9 @@ int sm_count() {
   return cached_sms;
 }
 
+static int g_forced_warps = 0;
+int debug_forced_warps() { return g_forced_warps; }
+
 void reverb_shutdown();  // reverb.cu
 
 }  // namespace dasp
@@ -40,5 +43,6 @@ int dasp_abi_version(void) { return DASP_ABI_VERSION; }
 const char* dasp_last_error(void) { return dasp::g_err; }
 int dasp_compiled_arch(void) { return 1000; }
 void dasp_shutdown(void) { dasp::reverb_shutdown(); }
+void dasp_debug_force_warps(int warps) { dasp::g_forced_warps = (warps == 1 || warps == 2 || warps == 4 || warps == 8) ? warps : 0; }
 
 }  // extern "C"

@@ -535,6 +535,7 @@ __global__ void eq_param_grad_kernel(const float* __restrict__ partial, const fl
 
 // ---- host side -----------------------------------------------------------------------------
 int pick_warps(int64_t rows) {
+  if (debug_forced_warps()) return debug_forced_warps() > 4 ? 4 : debug_forced_warps();
   const int64_t want = (int64_t)DASP_EQ_WARPS_PER_SM * sm_count();
   int w = 1;
   while (w < 4 && rows * w < want) w *= 2;

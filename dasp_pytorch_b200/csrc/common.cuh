@@ -55,6 +55,10 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
+// Test hook (dasp_debug_force_warps): 0 = automatic; 1/2/4/8 pins the warps-per-row choice of the scan kernels
+// so that every kernel variant can be exercised at small, cheap-to-check batch sizes.
+int debug_forced_warps();
+
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 

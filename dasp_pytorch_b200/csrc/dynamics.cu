@@ -511,6 +511,7 @@ int pick_warps(int64_t bs, int chs, int nbuf_per_ch) {
   const int64_t want = 16ll * sm_count();
   int w = 1;
   while (w < 8 && bs * w < want) w *= 2;
+  if (debug_forced_warps()) w = debug_forced_warps();
   while (w > 1 && (size_t)kStages * nbuf_per_ch * chs * (w * 32 * kE) * 4 + kSmemHeader > 96 * 1024) w /= 2;
   return w;
 }

@@ -40,6 +40,8 @@ const char* dasp_last_error(void);
 int dasp_compiled_arch(void);
 /* frees cached cuFFT plans and device-side filter-bank spectra */
 void dasp_shutdown(void);
+/* test hook: pin the warps-per-row variant of the scan kernels (1, 2, 4, 8; 0 = automatic choice) */
+void dasp_debug_force_warps(int warps);
 
 /* ---- gain: y = x * 10^(gain_db/20)            (reference functional.py:10-29) ------ */
 int dasp_gain_fwd(const float* x, const float* gain_db /* [bs] */, float* y, int64_t bs, int64_t chs,

@@ -62,23 +62,37 @@ def test_compressor_full_ranges_vs_oracle(cuda_device, bs, chs, n):
     _check(cuda_device, D.compressor, oracle.compressor, x, denorm(p01, COMP_RANGES))
 
 
-@pytest.mark.parametrize("bs,chs,n", [(2, 2, 4097), (3, 2, 100), (2, 1, 1), (2, 2, 224 * 8 + 4), (2400, 1, 512),
-                                      (700, 2, 1000), (1300, 2, 900)])
-def test_compressor_ragged_shapes(cuda_device, bs, chs, n):
-    """unaligned N (scalar path), N smaller than a tile, every warps-per-item variant.  At these
-    small N the reference's FFT grid time-aliases the smoother tail, so the arbiter here is the
-    oracle with an enlarged grid (fsm_tail: alias-free == true recursion, still differentiable)."""
+def _ragged_check(cuda_device, bs, chs, n, seed):
     import dasp_pytorch_b200 as D
-    x, p01 = _inputs(bs, chs, n, seed=6)
+    x, p01 = _inputs(bs, chs, n, seed=seed)
     params = denorm(p01, COMP_RANGES)
     y, dx, dp = run_with_grads(lambda xx, p: D.compressor(xx, SR, *p), x, params, torch.float32, cuda_device)
-    y64, dx64, dp64 = run_with_grads(lambda xx, p: oracle.compressor(xx, SR, *p, fsm_tail=1 << 17), x, params,
+    y64, dx64, dp64 = run_with_grads(lambda xx, p: oracle.compressor(xx, SR, *p, fsm_tail=1 << 16), x, params,
                                      torch.float64, "cpu")
     yt = oracle.compressor(x.double(), SR, *[p.double() for p in params], smoother="recursion")
     assert (peak_err(y64, yt) < 1e-9).all()          # enlarged grid == recursion
     assert (peak_err(y, y64) < TOL).all()
     assert (peak_err(dx, dx64) < TOL).all()
     assert (param_grad_err(dp, dp64) < 10 * TOL).all()
+
+
+@pytest.mark.parametrize("bs,chs,n", [(2, 2, 4097), (3, 2, 100), (2, 1, 1), (2, 2, 224 * 8 + 4), (5, 3, 3000)])
+def test_compressor_ragged_shapes(cuda_device, bs, chs, n):
+    """unaligned N (scalar path), N smaller than a tile, 3 channels.  At these small N the reference's FFT grid
+    time-aliases the smoother tail, so the arbiter here is the oracle with an enlarged grid (fsm_tail:
+    alias-free == true recursion, still differentiable)."""
+    _ragged_check(cuda_device, bs, chs, n, seed=6)
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+def test_compressor_every_warps_per_item_variant(cuda_device, warps):
+    """pin each warps-per-item kernel variant (test hook) on a small batch with several tiles + a ragged tail"""
+    from dasp_pytorch_b200 import _abi
+    _abi.lib().dasp_debug_force_warps(warps)
+    try:
+        _ragged_check(cuda_device, 3, 2, 224 * 8 * 2 + 36, seed=16 + warps)
+    finally:
+        _abi.lib().dasp_debug_force_warps(0)
 
 
 def test_compressor_lookahead_grads(cuda_device):

@@ -54,7 +54,7 @@ def test_eq_golden(cuda_device):
     assert param_grad_err(dp, ref)[1:].max() < TOL
 
 
-@pytest.mark.parametrize("bs,chs,n,low", [(16, 2, 48000, False), (16, 2, 48000, True), (5, 1, 48000, False)])
+@pytest.mark.parametrize("bs,chs,n,low", [(8, 2, 48000, False), (8, 2, 48000, True), (5, 1, 48000, False)])
 def test_eq_full_ranges_vs_oracle(cuda_device, bs, chs, n, low):
     """Processor parameter ranges (modules.py:136-155) at the BASELINE length; the sigma-form kernel is
     held to the STRICT 1e-4 here even where the reference's own fp32 path is 10-100x worse."""
@@ -63,20 +63,32 @@ def test_eq_full_ranges_vs_oracle(cuda_device, bs, chs, n, low):
     assert e.max() < 5e-5
 
 
-@pytest.mark.parametrize("bs,chs,n", [(2, 2, 4097), (3, 2, 100), (2, 1, 1), (2, 2, 480 * 4 + 4), (900, 2, 600),
-                                      (300, 2, 1000), (40, 3, 5000)])
+@pytest.mark.parametrize("bs,chs,n", [(2, 2, 4097), (3, 2, 100), (2, 1, 1), (2, 2, 480 * 4 + 4), (40, 3, 5000)])
 def test_eq_ragged_shapes(cuda_device, bs, chs, n):
-    """unaligned N (scalar path), N shorter than a tile, all warps-per-row variants, 3 channels.
+    """unaligned N (scalar path), N shorter than a tile, 3 channels.
     Arbiter: alias-free oracle (enlarged FFT grid == true recursion)."""
     x, p01 = _inputs(bs, chs, n, seed=4)
-    _check(cuda_device, x, denorm(p01, eq_ranges()), tail=1 << 18)
+    _check(cuda_device, x, denorm(p01, eq_ranges()), tail=1 << 16)
+
+
+@pytest.mark.parametrize("warps", [1, 2, 4])
+def test_eq_every_warps_per_row_variant(cuda_device, warps):
+    """the kernels pick 1/2/4 warps per row from the batch size; pin each variant (test hook) on a small batch
+    with several tiles and a ragged tail so that all three run at a size the oracle checks in seconds"""
+    from dasp_pytorch_b200 import _abi
+    x, p01 = _inputs(3, 2, 480 * 4 * 2 + 100, seed=14, low_corner=(warps == 2))
+    _abi.lib().dasp_debug_force_warps(warps)
+    try:
+        _check(cuda_device, x, denorm(p01, eq_ranges()), tail=1 << 16, strict=True)
+    finally:
+        _abi.lib().dasp_debug_force_warps(0)
 
 
 def test_eq_other_sample_rates_and_param_forms(cuda_device):
     import dasp_pytorch_b200 as D
     x, p01 = _inputs(4, 2, 24000, seed=9)
     for sr in (48000, 32000):
-        _check(cuda_device, x, denorm(p01, eq_ranges(sr)), sr=sr, tail=1 << 18)
+        _check(cuda_device, x, denorm(p01, eq_ranges(sr)), sr=sr, tail=1 << 16)
     # one-element parameters broadcast over the batch; integer cut-offs (examples/demo.py:44)
     xs = x.to(cuda_device)
     p = [torch.tensor([v], device=cuda_device) for v in (3.0, 200, 0.7, -2.0, 500, 1.0, 1.5, 3000, 2.0, -4.0, 9000,
