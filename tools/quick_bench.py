@@ -36,7 +36,7 @@ def timeit(fn, iters=10, warmup=3, flush=None):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--ops", default="dist,gain,comp,eq")
+    ap.add_argument("--ops", default="dist,gain,comp,eq,reverb")
     ap.add_argument("--bs", type=int, default=0)
     args = ap.parse_args()
     dev = torch.device("cuda:0")
@@ -83,6 +83,29 @@ def main():
         for bs in ([args.bs] if args.bs else [256, 1024]):
             p = [q.to(dev).requires_grad_(True) for q in denorm(torch.rand(bs, 18), eq_ranges())]
             run(f"parametric_eq_bs{bs}", bs, 2, 48000, lambda x: (lambda xx: D.parametric_eq(xx, SR, *p)))
+    if "reverb" in ops:
+        # BASELINE config 4: 256 x 2 x 48000, IR 96000, 1023 taps, device noise.  Algorithmic bytes:
+        # fwd 2*2N*4 + 2*2Leff*4, bwd 3*2N*4 + 2Leff*4 + 2*2Leff*4 + 2*12*Leff*4 per item (Leff = min(L, N))
+        bs, n, L = (args.bs or 256), 48000, 96000
+        leff = min(L, n)
+        p = [torch.rand(bs, device=dev).requires_grad_(True) for _ in range(25)]
+        x = (torch.rand(bs, 2, n, device=dev) * 2 - 1).requires_grad_(True)
+        fn = lambda xx: D.noise_shaped_reverberation(xx, SR, *p, num_samples=L, num_bandpass_taps=1023)
+        with torch.no_grad():
+            f_ms = timeit(lambda: fn(x.detach()), flush=flush)
+        gy = torch.rand(bs, 2, n, device=dev)
+
+        def fb():
+            fn(x).backward(gy)
+            x.grad = None
+        fb_ms = timeit(fb, flush=flush)
+        fwd_b = bs * (2 * 2 * n * 4 + 2 * 2 * leff * 4)
+        bwd_b = bs * (3 * 2 * n * 4 + 2 * leff * 4 + 2 * 2 * leff * 4 + 2 * 12 * leff * 4)
+        out["reverb_bs%d" % bs] = dict(shape=[bs, 2, n], ir=L, fwd_ms=f_ms, fwdbwd_ms=fb_ms,
+                                       fwd_frac=fwd_b / (f_ms * 1e-3) / 1e9 / PEAK,
+                                       bwd_frac=bwd_b / ((fb_ms - f_ms) * 1e-3) / 1e9 / PEAK,
+                                       gsamples_per_s=bs * 2 * n / (fb_ms * 1e-3) / 1e9)
+        print("reverb_bs%d" % bs, json.dumps(out["reverb_bs%d" % bs]), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/quick_bench.json", "w") as f:
         json.dump(out, f, indent=1)
