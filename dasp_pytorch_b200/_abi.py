@@ -41,6 +41,8 @@ _SIGNATURES = {
     "dasp_compiled_arch": (c_int, []),
     "dasp_shutdown": (None, []),
     "dasp_debug_force_warps": (None, [c_int]),
+    "dasp_debug_reverb_path": (None, [c_int]),
+    "dasp_debug_reverb_last_path": (c_int, []),
     "dasp_gain_fwd": (c_int, [P, P, P, I64, I64, I64, P]),
     "dasp_gain_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "dasp_distortion_fwd": (c_int, [P, P, P, I64, I64, P]),

@@ -32,6 +32,8 @@ int sm_count() {
 
 static int g_forced_warps = 0;
 int debug_forced_warps() { return g_forced_warps; }
+static int g_reverb_path = 0;
+int debug_reverb_path() { return g_reverb_path; }
 
 void reverb_shutdown();  // reverb.cu
 
@@ -44,5 +46,7 @@ const char* dasp_last_error(void) { return dasp::g_err; }
 int dasp_compiled_arch(void) { return 1000; }
 void dasp_shutdown(void) { dasp::reverb_shutdown(); }
 void dasp_debug_force_warps(int warps) { dasp::g_forced_warps = (warps == 1 || warps == 2 || warps == 4 || warps == 8) ? warps : 0; }
+
+void dasp_debug_reverb_path(int path) { dasp::g_reverb_path = (path == 1 || path == 2) ? path : 0; }
 
 }  // extern "C"

@@ -58,6 +58,9 @@ int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 // Test hook (dasp_debug_force_warps): 0 = automatic; 1/2/4/8 pins the warps-per-row choice of the scan kernels
 // so that every kernel variant can be exercised at small, cheap-to-check batch sizes.
 int debug_forced_warps();
+// Test hook (dasp_debug_reverb_path): IR synthesis of the device-noise reverb: 0 = automatic, 1 = generator / cuFFT /
+// shaping kernels, 2 = single cluster kernel
+int debug_reverb_path();
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

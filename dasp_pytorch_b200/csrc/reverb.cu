@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "fft8192.cuh"
 
 namespace dasp {
 namespace {
@@ -266,19 +267,14 @@ __device__ __forceinline__ float2 box_muller(unsigned a, unsigned b) {
 // e^{2 pi i m / R} for every polyphase factor R <= 16 (filled once per device on the host side)
 __constant__ float2 c_root[17][16];
 
-template <int R>
-__global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __restrict__ H1, int64_t item0, int nb,
-                                    unsigned long long seed) {
-  const int j1 = blockIdx.x * blockDim.x + threadIdx.x;       // residue class 0 .. nb/2
-  if (j1 > nb / 2) return;
-  const int k = blockIdx.y;
-  const int64_t il = blockIdx.z;
+// One residue class pair (j1, nb - j1) of one band signal: draws the R bins of each class, runs the R-point
+// DFT + twiddle ladder and hands  Q_b[j1], Q_b[nb - j1]  (b = 0 .. R-1) to `emit(b, q_j1, q_mirror)`.
+// Shared by the stand-alone generator kernel and the fused synthesis kernel, so both produce the same stream.
+template <int R, class Emit>
+__device__ __forceinline__ void spectral_unit(int j1, int nb, const float2* __restrict__ h, unsigned long long pair,
+                                              const PhiloxKeys& keys, Emit&& emit) {
   const int n1 = R * nb, n1h = n1 / 2;
-  const unsigned long long pair = (unsigned long long)((item0 + il) * kBands + k);
-  const float2* h = H1 + (int64_t)k * (n1h + 1);
   const float s_half = sqrtf(0.5f * (float)n1), s_full = sqrtf((float)n1);
-  const PhiloxKeys keys = philox_keys(seed);
-
   // value of the packed spectrum G_left + i G_right at bin j (0 <= j < n1) and at its mirror n1 - j
   // `canonical` (j <= n1/2) is a compile-time fact of the unrolled call site: for j1 in [0, nb/2] the bin
   // j1 + nb j2 lies in the lower half exactly when 2 j2 < R (the only tie, j = n1/2, is its own mirror)
@@ -299,7 +295,6 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
   };
 
   float2 ga[R], gb[R];
-  const bool self_mirror = (j1 == 0) || (2 * j1 == nb);     // class nb - j1 is class j1 itself
 #pragma unroll
   for (int j2 = 0; j2 < R; ++j2) {
     float2 a, m;
@@ -323,7 +318,6 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
   sincospif(2.0f * (float)(nb - j1) / (float)n1, &w1b.y, &w1b.x);
   const float2 wx = make_float2(w1a.x, w1b.x), wy = make_float2(w1a.y, w1b.y), nwy = make_float2(-w1a.y, -w1b.y);
   float2 tx = make_float2(1.f, 1.f), ty = make_float2(0.f, 0.f);      // twiddle e^{2 pi i j b / n1}, both classes
-  float2* outp = C + ((il * kBands + k) * R) * (int64_t)nb;
 #pragma unroll
   for (int b = 0; b < R; ++b) {
     float2 sre = make_float2(0.f, 0.f), sim = make_float2(0.f, 0.f);
@@ -335,16 +329,46 @@ __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __rest
     }
     const float2 ore = __ffma2_rn(sre, tx, __fmul2_rn(sim, make_float2(-ty.x, -ty.y)));
     const float2 oim = __ffma2_rn(sre, ty, __fmul2_rn(sim, tx));
-    outp[(int64_t)b * nb + j1] = make_float2(ore.x, oim.x);
-    if (!self_mirror) outp[(int64_t)b * nb + (nb - j1)] = make_float2(ore.y, oim.y);
+    emit(b, make_float2(ore.x, oim.x), make_float2(ore.y, oim.y));
     const float2 ntx = __ffma2_rn(tx, wx, __fmul2_rn(ty, nwy));
     ty = __ffma2_rn(tx, wy, __fmul2_rn(ty, wx));
     tx = ntx;
   }
 }
 
+// PLANAR == false: C[((item*12 + k)*R + b)*nb + j] = (re, im) pairs, the input layout of the batched cuFFT C2C.
+// PLANAR == true : the same 64 KB block per (item, band, class) holds [re plane nb][im plane nb] -- the shared-memory
+//                  layout of fft8192.cuh, so ifft_shape_kernel can fetch a class with plain bulk copies.
+template <int R, bool PLANAR>
+__global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __restrict__ H1, int64_t item0, int nb,
+                                    unsigned long long seed) {
+  const int j1 = blockIdx.x * blockDim.x + threadIdx.x;       // residue class 0 .. nb/2
+  if (j1 > nb / 2) return;
+  const int k = blockIdx.y;
+  const int64_t il = blockIdx.z;
+  const unsigned long long pair = (unsigned long long)((item0 + il) * kBands + k);
+  const PhiloxKeys keys = philox_keys(seed);
+  const bool self_mirror = (j1 == 0) || (2 * j1 == nb);     // class nb - j1 is class j1 itself
+  float2* outp = C + ((il * kBands + k) * R) * (int64_t)nb;
+  spectral_unit<R>(j1, nb, H1 + (int64_t)k * (R * nb / 2 + 1), pair, keys, [&](int b, float2 q, float2 qm) {
+    if (PLANAR) {
+      float* pl = reinterpret_cast<float*>(outp + (int64_t)b * nb);
+      pl[j1] = q.x; pl[nb + j1] = q.y;
+      if (!self_mirror) { pl[nb - j1] = qm.x; pl[2 * nb - j1] = qm.y; }
+    } else {
+      outp[(int64_t)b * nb + j1] = q;
+      if (!self_mirror) outp[(int64_t)b * nb + (nb - j1)] = qm;
+    }
+  });
+}
+
 // torch.linspace(0, 1, L) in fp32 (functional.py:561): symmetric fill around the midpoint
 __device__ __forceinline__ float time_axis(int64_t t, int64_t L, float step) {
+  return (t < L / 2) ? step * (float)t : 1.0f - step * (float)(L - 1 - t);
+}
+
+// same values for L < 2^31 without 64-bit integer conversions
+__device__ __forceinline__ float time_axis32(int t, int L, float step) {
   return (t < L / 2) ? step * (float)t : 1.0f - step * (float)(L - 1 - t);
 }
 
@@ -408,6 +432,225 @@ __global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __
     ar = fmaf(e, v[k].y, ar);
   }
   Hb[il * (int64_t)jb * kNbA + (t / kB) * kNbA + (t % kB)] = make_float2(al, ar);
+}
+
+// ---- inverse FFT + envelope / gain / band mean as one kernel (device-noise mode, nb == 8192) -----------
+// Replaces the batched cuFFT C2C + shape_ir_pp_kernel pair: the generator's spectrum is read ONCE (bulk copies
+// straight into the planar shared-memory layout of fft8192.cuh, double buffered across the 12 bands), transformed
+// in shared memory, and each thread accumulates  gain_k env_k(t) f_k(t) / 12  for its 16 taps in registers.  The
+// filtered noise f is written back (over the consumed spectrum block, as (left, right) pairs) only when the
+// backward needs it.  grid = (R, items): CTA (c, item) owns polyphase class c, i.e. the IR taps R a + c.
+constexpr int kFusedThreads = fft8k::kThreads;
+constexpr int kFusedSmemFloats = 2 * 2 * fft8k::kPlaneG + 2 * fft8k::kPlaneY + fft8k::kTabFloats + 32;
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+ifft_shape_kernel(float* __restrict__ Cpl, const float* __restrict__ twiddles, const float* __restrict__ params,
+                  float2* __restrict__ Hb, int save_f, int L, int leff, int jb, int R) {
+  constexpr int nb = fft8k::kN;
+  extern __shared__ __align__(128) float sm[];
+  float* G = sm;                                   // [buffer][re, im][8192]
+  float* Yr = sm + 4 * fft8k::kPlaneG;
+  float* Yi = Yr + fft8k::kPlaneY;
+  float* tabf = Yi + fft8k::kPlaneY;
+  float* gk = tabf + fft8k::kTabFloats;
+  float* rk = gk + 16;
+  uint64_t* full = reinterpret_cast<uint64_t*>(rk + 16);
+  const int t = threadIdx.x, c = blockIdx.x;
+  const int64_t il = blockIdx.y;
+  float* blk = Cpl + ((il * kBands) * R + c) * (int64_t)(2 * nb);      // band k at blk + k * R * 2 nb
+  const int64_t band_stride = (int64_t)R * 2 * nb;
+
+  if (t == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+  }
+  for (int e = t; e < fft8k::kTabFloats; e += kFusedThreads) tabf[e] = twiddles[e];
+  if (t < kBands) {
+    gk[t] = params[il * 25 + t] * (1.0f / kBands);
+    rk[t] = -(params[il * 25 + kBands + t] * 10.0f + 1.0f);
+  }
+  __syncthreads();
+  auto fetch = [&](int k) {                        // thread 0: 64 KB spectrum block of band k -> G[k & 1]
+    uint64_t* bar = &full[k & 1];
+    float* dst = G + (k & 1) * 2 * fft8k::kPlaneG;
+    const float* src = blk + k * band_stride;
+    mbar_arrive_expect_tx(bar, 2u * nb * 4u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tma_load_1d(dst + i * 4096, src + i * 4096, 16384u, bar);
+  };
+  if (t == 0) { fetch(0); fetch(1); }
+  const fft8k::Tables tb = fft8k::carve_tables(tabf);
+  const float step = 1.0f / (float)(L - 1);
+  float accr[16], acci[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) { accr[q] = 0.f; acci[q] = 0.f; }
+
+  for (int k = 0; k < kBands; ++k) {
+    mbar_wait(&full[k & 1], (uint32_t)((k >> 1) & 1));
+    float* gr = G + (k & 1) * 2 * fft8k::kPlaneG;
+    float* gi = gr + fft8k::kPlaneG;
+    fft8k::p1<true>(gr, gi, tb, t);
+    __syncthreads();
+    fft8k::p2<true>(gr, gi, Yr, Yi, tb, t);
+    fence_proxy_async_smem();                      // pass-1 stores to G (generic proxy) before the bulk refill
+    __syncthreads();
+    if (t == 0 && k + 2 < kBands) fetch(k + 2);
+    fft8k::P3Regs q3;
+    fft8k::p3_load<true>(Yr, Yi, t, q3);
+    __syncthreads();
+    fft8k::p3_store<true>(Yr, Yi, tb, t, q3);
+    __syncthreads();
+    float xr[16], xi[16];
+    fft8k::p4<true>(Yr, Yi, t, xr, xi);
+    const float g = gk[k], rr = rk[k];
+    float2* fout = reinterpret_cast<float2*>(blk + k * band_stride);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int a = t + 512 * q;
+      const float e = g * __expf(rr * time_axis32(R * a + c, L, step));
+      accr[q] = fmaf(e, xr[q], accr[q]);
+      acci[q] = fmaf(e, xi[q], acci[q]);
+      if (save_f) fout[a] = make_float2(xr[q], xi[q]);
+    }
+    // (Y is next written by pass 2 of the following band, behind the barrier after its pass 1)
+  }
+  float2* out = Hb + il * (int64_t)jb * kNbA;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int tau = R * (t + 512 * q) + c;
+    if (tau < leff) out[(tau / kB) * kNbA + (tau % kB)] = make_float2(accr[q], acci[q]);
+  }
+}
+
+// ---- fused IR synthesis (device-noise mode, nb == 8192, R <= 8) -------------------------------------
+// spectral_gen -> inverse FFT -> shape/accumulate as ONE kernel, so the 4.7 MB-per-item filtered-noise buffer is
+// written at most once (for the backward) instead of being written, transformed in place and read back.
+//
+// One thread-block CLUSTER of R CTAs per item; CTA c owns polyphase class c, i.e. the IR taps R a + c.
+//   * generation: the 12 * (nb/2 + 1) class pairs of the item are dealt round-robin over the R * 512 threads of
+//     the cluster (so every thread draws the same number of units); a unit's R results go to the R CTAs of the
+//     cluster as remote shared-memory stores (DSMEM) into the band's spectrum buffer G[band & 1] (planar re / im).
+//   * as soon as a band is complete (cluster barrier), every CTA runs the in-shared-memory inverse FFT of its
+//     class (fft8192.cuh) and accumulates  gain_k env_k(t) f_k(t) / 12  for its 16 taps per thread in registers;
+//     f is stored for the backward only when the caller keeps it.
+//   * G is double buffered by band parity: a second (split arrive / wait) cluster barrier hands a buffer back to
+//     the generators once every CTA has finished reading it (after FFT pass 2).
+constexpr int kMaxFusedR = 8;
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+// generic pointer to the same shared-memory location in CTA `rank` of the cluster (DSMEM).  Kept 64-bit/generic on
+// purpose: with 32-bit shared::cluster addresses ptxas folded "+ 4 nb" of the mirror index into the store's
+// immediate AFTER widening (base - 4 j1) to 64 bits, which wraps for rank 0 and faults.
+__device__ __forceinline__ float* map_to_cta(float* smem_ptr, unsigned rank) {
+  uint64_t r;
+  asm volatile("mapa.u64 %0, %1, %2;" : "=l"(r) : "l"(reinterpret_cast<uint64_t>(smem_ptr)), "r"(rank));
+  return reinterpret_cast<float*>(r);
+}
+
+template <int R>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+ir_synth_fused_kernel(const float2* __restrict__ H1, const float* __restrict__ twiddles,
+                      const float* __restrict__ params, float2* __restrict__ Hb, float2* __restrict__ Csave, int64_t item0, int64_t L, int64_t leff, int jb,
+                      unsigned long long seed) {
+  constexpr int nb = fft8k::kN, U = nb / 2 + 1, CT = R * kFusedThreads, total = kBands * U;
+  static_assert(CT < U, "at most one band may complete per generation round");
+  extern __shared__ __align__(16) float sm[];
+  float* G = sm;                                   // [parity][re, im][8192]
+  float* Yr = sm + 4 * fft8k::kPlaneG;
+  float* Yi = Yr + fft8k::kPlaneY;
+  float* tabf = Yi + fft8k::kPlaneY;
+  float* gk = tabf + fft8k::kTabFloats;
+  float* rk = gk + 16;
+  const int t = threadIdx.x;
+  const unsigned c = cluster_ctarank();
+  const int64_t il = blockIdx.y;
+
+  for (int e = t; e < fft8k::kTabFloats; e += kFusedThreads) tabf[e] = twiddles[e];
+  if (t < kBands) {
+    gk[t] = params[il * 25 + t] * (1.0f / kBands);
+    rk[t] = -(params[il * 25 + kBands + t] * 10.0f + 1.0f);
+  }
+  const fft8k::Tables tb = fft8k::carve_tables(tabf);
+  float* remote[R];                                // G of every CTA of the cluster
+#pragma unroll
+  for (int b = 0; b < R; ++b) remote[b] = map_to_cta(G, (unsigned)b);
+  const PhiloxKeys keys = philox_keys(seed);
+  const float step = 1.0f / (float)(L - 1);
+  float accr[16], acci[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) { accr[q] = 0.f; acci[q] = 0.f; }
+  // every CTA of the cluster must be resident (and its tables written) before the first remote store
+  cluster_arrive();
+  cluster_wait();
+
+  int processed = 0;
+  bool buffer_handed_back = false;                 // an arrive of the "G is free" barrier is outstanding
+  constexpr int rounds = (total + CT - 1) / CT;
+  for (int r = 0; r < rounds; ++r) {
+    if (buffer_handed_back) { cluster_wait(); buffer_handed_back = false; }
+    const int u = r * CT + (int)c * kFusedThreads + t;
+    if (u < total) {
+      const int k = u / U, j1 = u - k * U;
+      const unsigned long long pair = (unsigned long long)((item0 + il) * kBands + k);
+      const bool self_mirror = (j1 == 0) || (2 * j1 == nb);
+      const int off = (k & 1) * 2 * fft8k::kPlaneG;
+      spectral_unit<R>(j1, nb, H1 + (int64_t)k * (R * nb / 2 + 1), pair, keys, [&](int b, float2 q, float2 qm) {
+        float* base = remote[b] + off;
+        base[j1] = q.x;
+        base[fft8k::kPlaneG + j1] = q.y;
+        if (!self_mirror) {
+          base[nb - j1] = qm.x;
+          base[fft8k::kPlaneG + nb - j1] = qm.y;
+        }
+      });
+    }
+    const int done = (r + 1) * CT < total ? (r + 1) * CT : total;
+    if (done / U > processed) {                    // band `processed` is complete in every CTA's G
+      cluster_arrive();
+      cluster_wait();
+      const int kk = processed;
+      float* gr = G + (kk & 1) * 2 * fft8k::kPlaneG;
+      float* gi = gr + fft8k::kPlaneG;
+      fft8k::p1<true>(gr, gi, tb, t);
+      __syncthreads();
+      fft8k::p2<true>(gr, gi, Yr, Yi, tb, t);
+      __syncthreads();
+      cluster_arrive();                            // this CTA no longer reads G[kk & 1]
+      buffer_handed_back = true;
+      fft8k::P3Regs q3;
+      fft8k::p3_load<true>(Yr, Yi, t, q3);
+      __syncthreads();
+      fft8k::p3_store<true>(Yr, Yi, tb, t, q3);
+      __syncthreads();
+      float xr[16], xi[16];
+      fft8k::p4<true>(Yr, Yi, t, xr, xi);
+      const float g = gk[kk], rr = rk[kk];
+      float2* fout = Csave ? Csave + ((il * kBands + kk) * R + c) * (int64_t)nb : nullptr;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int a = t + 512 * q;
+        const float e = g * __expf(rr * time_axis((int64_t)R * a + c, L, step));
+        accr[q] = fmaf(e, xr[q], accr[q]);
+        acci[q] = fmaf(e, xi[q], acci[q]);
+        if (fout) fout[a] = make_float2(xr[q], xi[q]);
+      }
+      ++processed;     // (Y is next written by pass 2 of the following band, behind a cluster barrier)
+    }
+  }
+  if (buffer_handed_back) cluster_wait();
+  float2* out = Hb + il * (int64_t)jb * kNbA;
+#pragma unroll
+  for (int q = 0; q < 16; ++q) {
+    const int64_t tau = (int64_t)R * (t + 512 * q) + c;
+    if (tau < leff) out[(tau / kB) * kNbA + (tau % kB)] = make_float2(accr[q], acci[q]);
+  }
 }
 
 // part[((item*nparts + blockIdx.x)*12 + k)*2 + {0,1}], nparts = gridDim.x; threads stride over time
@@ -792,15 +1035,16 @@ int get_filterbank_n1(const Geom& g, double sr, cudaStream_t st, const float2** 
 
 template <int R>
 void launch_spectral(float2* C, const float2* H1, int64_t item0, int64_t items, int nb, unsigned long long seed,
-                     cudaStream_t st) {
+                     bool planar, cudaStream_t st) {
   const int threads = 128;
   dim3 grid((unsigned)((nb / 2 + 1 + threads - 1) / threads), kBands, (unsigned)items);
-  spectral_gen_kernel<R><<<grid, threads, 0, st>>>(C, H1, item0, nb, seed);
+  if (planar) spectral_gen_kernel<R, true><<<grid, threads, 0, st>>>(C, H1, item0, nb, seed);
+  else        spectral_gen_kernel<R, false><<<grid, threads, 0, st>>>(C, H1, item0, nb, seed);
 }
 bool dispatch_spectral(int R, float2* C, const float2* H1, int64_t item0, int64_t items, int nb,
-                       unsigned long long seed, cudaStream_t st) {
+                       unsigned long long seed, bool planar, cudaStream_t st) {
   switch (R) {
-#define DASP_R(r) case r: launch_spectral<r>(C, H1, item0, items, nb, seed, st); return true;
+#define DASP_R(r) case r: launch_spectral<r>(C, H1, item0, items, nb, seed, planar, st); return true;
     DASP_R(1) DASP_R(2) DASP_R(3) DASP_R(4) DASP_R(5) DASP_R(6) DASP_R(7) DASP_R(8) DASP_R(9) DASP_R(10)
     DASP_R(11) DASP_R(12) DASP_R(13) DASP_R(14) DASP_R(15) DASP_R(16)
 #undef DASP_R
@@ -808,6 +1052,91 @@ bool dispatch_spectral(int R, float2* C, const float2* H1, int64_t item0, int64_
   }
 }
 constexpr int kMaxSpectralR = 16;
+
+// fused synthesis: one cluster of R CTAs per item.  Returns false when the device cannot co-schedule such a
+// cluster (then the three-kernel path is used), true after a launch attempt (check cudaGetLastError).
+// twiddle tables of fft8192.cuh (fp64 on the host, once per device)
+std::map<int, float*> g_fft_tab;
+int get_fft_tables(cudaStream_t st, const float** out) {
+  int dev = 0;
+  DASP_CUDA_OK(cudaGetDevice(&dev));
+  auto it = g_fft_tab.find(dev);
+  if (it == g_fft_tab.end()) {
+    std::vector<float> h(fft8k::kTabFloats, 0.f);
+    for (int e = 0; e < fft8k::kTabEntries; ++e) {
+      int co, so, dup;
+      double turns;
+      fft8k::table_entry(e, co, so, dup, turns);
+      const float c = (float)cos(2.0 * kPi * turns), sn = (float)sin(2.0 * kPi * turns);
+      h[co] = c; h[so] = sn;
+      if (dup) { h[co + 1] = c; h[so + 1] = sn; }
+    }
+    float* d = nullptr;
+    DASP_CUDA_OK(cudaMalloc(&d, sizeof(float) * h.size()));
+    DASP_CUDA_OK(cudaMemcpyAsync(d, h.data(), sizeof(float) * h.size(), cudaMemcpyHostToDevice, st));
+    DASP_CUDA_OK(cudaStreamSynchronize(st));   // one-off cache fill (h goes out of scope)
+    it = g_fft_tab.emplace(dev, d).first;
+  }
+  *out = it->second;
+  return DASP_OK;
+}
+int launch_ifft_shape(float2* C, const float* tw, const float* params, float2* hs, bool save_f, int64_t items,
+                      const Geom& g, int jb, cudaStream_t st) {
+  const size_t smem = sizeof(float) * kFusedSmemFloats + 2 * sizeof(uint64_t);
+  static std::map<int, bool> configured;             // per device, guarded by g_mu
+  int dev = 0;
+  DASP_CUDA_OK(cudaGetDevice(&dev));
+  if (!configured[dev]) {
+    DASP_CUDA_OK(cudaFuncSetAttribute(ifft_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[dev] = true;
+  }
+  ifft_shape_kernel<<<dim3((unsigned)g.rpp, (unsigned)items), kFusedThreads, smem, st>>>(
+      reinterpret_cast<float*>(C), tw, params, hs, save_f ? 1 : 0, (int)g.L, (int)g.leff, jb, (int)g.rpp);
+  DASP_LAUNCH_OK("ifft_shape_kernel");
+  return DASP_OK;
+}
+int g_last_fused = 0;                                // test hook: IR-synthesis path of the last forward chunk
+std::map<std::pair<int, int>, int> g_fused_ok;      // (device, R) -> clusters that fit, guarded by g_mu
+template <int R>
+bool launch_fused(const float2* H1, const float* tw, const float* params, float2* hs, float2* Csave, int64_t item0, int64_t items,
+                  int64_t L, int64_t leff, int jb, unsigned long long seed, cudaStream_t st) {
+  auto kern = ir_synth_fused_kernel<R>;
+  const size_t smem = sizeof(float) * kFusedSmemFloats;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(R, (unsigned)items, 1);
+  cfg.blockDim = dim3(kFusedThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = R; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto it = g_fused_ok.find({dev, R});
+  if (it == g_fused_ok.end()) {
+    int n = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+      n = 0;
+      cudaGetLastError();
+    }
+    it = g_fused_ok.emplace(std::make_pair(dev, R), n).first;
+  }
+  if (it->second < 1) return false;
+  cudaLaunchKernelEx(&cfg, kern, H1, tw, params, hs, Csave, item0, L, leff, jb, seed);
+  return true;
+}
+bool dispatch_fused(int R, const float2* H1, const float* tw, const float* params, float2* hs, float2* Csave, int64_t item0,
+                    int64_t items, int64_t L, int64_t leff, int jb, unsigned long long seed, cudaStream_t st) {
+  switch (R) {
+#define DASP_R(r) case r: return launch_fused<r>(H1, tw, params, hs, Csave, item0, items, L, leff, jb, seed, st);
+    DASP_R(1) DASP_R(2) DASP_R(3) DASP_R(4) DASP_R(5) DASP_R(6) DASP_R(7) DASP_R(8)
+#undef DASP_R
+    default: return false;
+  }
+}
 
 struct Plans { PlanVal blk_c2c, pp_c2c, xi_c2c, hj_c2c; size_t work; };
 int get_plans(const Geom& g, int64_t items, Plans& p) {
@@ -870,6 +1199,8 @@ void reverb_shutdown() {
   g_plans.clear();
   for (auto& kv : g_fb) cudaFree(kv.second);
   g_fb.clear();
+  for (auto& kv : g_fft_tab) cudaFree(kv.second);
+  g_fft_tab.clear();
 }
 
 }  // namespace dasp
@@ -877,6 +1208,8 @@ void reverb_shutdown() {
 using namespace dasp;
 
 extern "C" {
+
+int dasp_debug_reverb_last_path(void) { return g_last_fused; }
 
 // host-side restatement of signal.octave_band_filterbank: writes 12*taps floats (no GPU needed)
 int dasp_reverb_filterbank(int64_t taps, double sample_rate, float* out) {
@@ -971,9 +1304,33 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
 
     // ---- IR synthesis: (left, right) taps land in the zero-initialised partition layout hs ----
     DASP_CUDA_OK(cudaMemsetAsync(hs, 0, sizeof(float2) * items * J * kNbA, st));
-    if (spectral) {
+    // device-noise IR synthesis, three variants (same Philox stream, so they agree to transform rounding):
+    //   2 = generator -> ifft_shape_kernel (own in-shared-memory FFT fused with the shaping; default for nb == 8192)
+    //   1 = one thread-block cluster per item (generator + FFT + shaping in one kernel; dasp_debug_reverb_path(2))
+    //   0 = generator -> batched cuFFT -> shape_ir_pp_kernel (dasp_debug_reverb_path(1), and any other nb)
+    int synth = 0;
+    const bool own_fft = spectral && nb == fft8k::kN && g.L < (int64_t)1 << 31;
+    if (own_fft && debug_reverb_path() == 2 && g.rpp <= kMaxFusedR) synth = 1;
+    else if (own_fft && debug_reverb_path() != 1) synth = 2;
+    const float* tw = nullptr;
+    if (synth != 0 && (rc = get_fft_tables(st, &tw)) != DASP_OK) return rc;
+    if (synth == 1) {
+      if (dispatch_fused((int)g.rpp, H1, tw, params + item0 * 25, hs, f_save ? C : nullptr, item0, items, g.L, g.leff, J,
+                         (unsigned long long)seed, st)) {
+        DASP_LAUNCH_OK("ir_synth_fused_kernel");
+      } else {
+        synth = 2;                                   // the device cannot co-schedule such a cluster
+      }
+    }
+    g_last_fused = synth;
+    if (synth == 1) {
+    } else if (synth == 2) {
+      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, (unsigned long long)seed, /*planar=*/true, st);
+      DASP_LAUNCH_OK("spectral_gen_kernel");
+      if ((rc = launch_ifft_shape(C, tw, params + item0 * 25, hs, f_save != nullptr, items, g, J, st)) != DASP_OK) return rc;
+    } else if (spectral) {
       // device noise: draw the filtered spectrum directly, one inverse transform (polyphase layout)
-      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, (unsigned long long)seed, st);
+      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, (unsigned long long)seed, /*planar=*/false, st);
       DASP_LAUNCH_OK("spectral_gen_kernel");
       DASP_CUFFT_OK(cufftSetStream(pl.pp_c2c.h, st));
       DASP_CUFFT_OK(cufftSetWorkArea(pl.pp_c2c.h, ws_cufft));

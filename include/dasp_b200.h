@@ -42,6 +42,13 @@ int dasp_compiled_arch(void);
 void dasp_shutdown(void);
 /* test hook: pin the warps-per-row variant of the scan kernels (1, 2, 4, 8; 0 = automatic choice) */
 void dasp_debug_force_warps(int warps);
+/* test hook, IR synthesis of the device-noise reverb (all variants draw the same Philox stream and must agree):
+   0 = automatic (generator -> fused in-shared-memory inverse FFT + shaping kernel when the block FFT is 8192 points),
+   1 = generator -> batched cuFFT -> shaping kernel, 2 = one thread-block-cluster kernel per item */
+void dasp_debug_reverb_path(int path);
+/* test hook: variant used by the last chunk of the most recent dasp_reverb_fwd: 0 = cuFFT pipeline, 1 = cluster
+   kernel, 2 = generator + fused FFT/shaping kernel */
+int dasp_debug_reverb_last_path(void);
 
 /* ---- gain: y = x * 10^(gain_db/20)            (reference functional.py:10-29) ------ */
 int dasp_gain_fwd(const float* x, const float* gain_db /* [bs] */, float* y, int64_t bs, int64_t chs,

@@ -172,3 +172,50 @@ def test_reverb_contract(cuda_device):
     torch.manual_seed(1)
     y2 = D.noise_shaped_reverberation(x, SR, *p, num_samples=256, num_bandpass_taps=31)
     assert torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("n,L", [(4000, 6000), (12000, 30000), (20000, 20000), (30000, 40000), (36000, 36000),
+                                 (48000, 96000), (50000, 50000), (60000, 60000), (70000, 80000)])
+def test_reverb_ir_synthesis_variants_agree(cuda_device, n, L):
+    """Three device implementations of the device-noise IR synthesis draw the same Philox stream, so for one seed they
+    must agree to transform rounding -- output, saved filtered noise (through the parameter gradients) and dL/dx:
+      0: generator -> batched cuFFT -> shaping kernel,
+      2: generator -> own in-shared-memory 8192-point inverse FFT fused with the shaping (the default),
+      1: one thread-block cluster of R CTAs per item doing all three steps (R <= 8).
+    The cases cover polyphase factors R = 1 ... 9."""
+    import dasp_pytorch_b200 as D
+    from dasp_pytorch_b200 import _abi
+    bs, taps = 3, 1023
+    R = -(-(min(n, L) + taps - 1) // 8192)
+    g = torch.Generator().manual_seed(n)
+    x = (torch.rand(bs, 2, n, generator=g) * 2 - 1).to(cuda_device)
+    x[0, :, 1:] = 0.0                                          # item 0: an impulse -> its wet signal is the IR itself
+    w = torch.randn(bs, 2, n, generator=g).to(cuda_device)
+    p = [q.to(cuda_device) for q in _params01(bs, 3)]
+    p[24] = torch.full((bs,), 0.9, device=cuda_device)
+
+    def run(path):
+        _abi.lib().dasp_debug_reverb_path(path)
+        try:
+            torch.manual_seed(77)
+            xx = x.clone().requires_grad_(True)
+            pp = [q.clone().requires_grad_(True) for q in p]
+            y = D.noise_shaped_reverberation(xx, SR, *pp, num_samples=L, num_bandpass_taps=taps)
+            used = _abi.lib().dasp_debug_reverb_last_path()
+            (y * w).sum().backward()
+            torch.manual_seed(77)
+            with torch.no_grad():                               # forward that keeps nothing for a backward
+                y_inf = D.noise_shaped_reverberation(x, SR, *p, num_samples=L, num_bandpass_taps=taps)
+            assert torch.equal(y.detach(), y_inf)
+            return used, y.detach(), xx.grad, torch.stack([q.grad for q in pp], 1)
+        finally:
+            _abi.lib().dasp_debug_reverb_path(0)
+
+    used_ref, y_ref, dx_ref, dp_ref = run(1)
+    assert used_ref == 0 and y_ref.abs().max() > 1e-3
+    for path, expect in ((0, 2), (2, 1 if R <= 8 else 2)):
+        used, y, dx, dp = run(path)
+        assert used == expect, (path, used)
+        assert peak_err(y, y_ref).max() < 2e-5, (path, peak_err(y, y_ref))
+        assert peak_err(dx, dx_ref).max() < 2e-5, (path, peak_err(dx, dx_ref))
+        assert float((dp - dp_ref).abs().max() / dp_ref.abs().max()) < 2e-5, path
