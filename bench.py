@@ -371,10 +371,14 @@ def main():
         }
         kern = {"eq_fwd": "eq_fwd_kernel", "eq_bwd": "eq_bwd_kernel", "comp_fwd": "dynamics_fwd_kernel",
                 "comp_bwd": "dynamics_bwd_kernel", "dist_fwd": "pointwise_fwd_kernel", "dist_bwd": "pointwise_bwd_kernel",
-                "reverb_fwd": "reverb fwd pipeline: spectral_gen_kernel, cuFFT C2C(8192) x4, shape_ir_pp_kernel, "
-                              "x_blocks_kernel, partition_mac_kernel, mix_blocks_kernel",
+                "reverb_fwd": "reverb fwd pipeline: spectral_gen_kernel, ifft_shape_kernel (own in-shared-memory FFT), "
+                              "x_blocks_kernel, cuFFT C2C(8192) x3, partition_mac_kernel, mix_blocks_kernel",
                 "reverb_bwd": "reverb bwd pipeline: g_blocks_kernel, cuFFT C2C(8192) x3, partition_mac_kernel x2, "
                               "finish_dx_blocks_kernel, ir_grad_pp_kernel"}
+        # DRAM bytes per item actually moved by the two reverb pipelines: dram__bytes_read.sum + dram__bytes_write.sum
+        # summed over their kernels in one `ncu --set full` capture of a 128-item chunk at this geometry
+        # (profiles/r01_reverb_kernels_b128_full.md: fwd 1265 + 1434 MB, bwd 1636 + 359 MB per 128 items)
+        traffic_item = {"reverb_fwd": 21.09e6, "reverb_bwd": 15.59e6} if (N_SAMPLES, IR_LEN) == (48000, 96000) else {}
         breakdown = {}
         for name, v in stages.items():
             m = statistics.mean(v)
@@ -384,7 +388,8 @@ def main():
         roofline = None
         if dom:
             roofline = {"bound": "hbm", "kernel": kern[dom], "achieved": breakdown[dom]["alg_GBps"], "peak": peak,
-                        "unit": "GB/s", "frac": breakdown[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                        "unit": "GB/s", "frac": breakdown[dom]["frac"],
+                        "traffic": traffic_item[dom] * bs if dom in traffic_item else None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": breakdown[dom]["ms"]}
         chunks = -(-bs // F.REVERB_CHUNK_ITEMS)
         own_launches_per_step = 1 + 2 + 1 + 1 + 1 + 2 + chunks * (5 + 6)   # eq f/b, comp f/b, dist f/b, reverb per chunk
