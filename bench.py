@@ -371,8 +371,9 @@ def main():
         }
         kern = {"eq_fwd": "eq_fwd_kernel", "eq_bwd": "eq_bwd_kernel", "comp_fwd": "dynamics_fwd_kernel",
                 "comp_bwd": "dynamics_bwd_kernel", "dist_fwd": "pointwise_fwd_kernel", "dist_bwd": "pointwise_bwd_kernel",
-                "reverb_fwd": "reverb fwd pipeline: spectral_gen_kernel, ifft_shape_kernel (own in-shared-memory FFT), "
-                              "x_blocks_kernel, cuFFT C2C(8192) x3, partition_mac_kernel, mix_blocks_kernel",
+                "reverb_fwd": "reverb fwd pipeline: spectral_gen_kernel, ifft_shape_kernel, x_fft_kernel, partition_mac_kernel, "
+                              "ifft_mix_kernel (own in-shared-memory 8192-point FFT fused with the element-wise stages), "
+                              "cuFFT C2C(8192) x1 (IR partitions)",
                 "reverb_bwd": "reverb bwd pipeline: g_blocks_kernel, cuFFT C2C(8192) x3, partition_mac_kernel x2, "
                               "finish_dx_blocks_kernel, ir_grad_pp_kernel"}
         # DRAM bytes per item actually moved by the two reverb pipelines: dram__bytes_read.sum + dram__bytes_write.sum

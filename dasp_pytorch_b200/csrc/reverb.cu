@@ -442,6 +442,7 @@ __global__ void shape_ir_pp_kernel(const float2* __restrict__ C, const float* __
 // backward needs it.  grid = (R, items): CTA (c, item) owns polyphase class c, i.e. the IR taps R a + c.
 constexpr int kFusedThreads = fft8k::kThreads;
 constexpr int kFusedSmemFloats = 2 * 2 * fft8k::kPlaneG + 2 * fft8k::kPlaneY + fft8k::kTabFloats + 32;
+constexpr size_t kFftSmemBytes = sizeof(float) * kFusedSmemFloats + 2 * sizeof(uint64_t);   // + the two mbarriers
 
 __global__ void __launch_bounds__(kFusedThreads, 1)
 ifft_shape_kernel(float* __restrict__ Cpl, const float* __restrict__ twiddles, const float* __restrict__ params,
@@ -520,6 +521,141 @@ ifft_shape_kernel(float* __restrict__ Cpl, const float* __restrict__ twiddles, c
   for (int q = 0; q < 16; ++q) {
     const int tau = R * (t + 512 * q) + c;
     if (tau < leff) out[(tau / kB) * kNbA + (tau % kB)] = make_float2(accr[q], acci[q]);
+  }
+}
+
+// ---- block transforms of the audio convolution on the same in-shared-memory FFT ---------------------------
+// Persistent CTAs (one per SM) walk the (item, block) list; the input of block m + 2 is bulk-copied into the free
+// half of the double buffer while block m is transformed, so the copy engine, the FFT and the epilogue stores overlap.
+struct FftSmem {
+  float* G; float* Yr; float* Yi; float* tabf; uint64_t* full;
+  __device__ __forceinline__ explicit FftSmem(float* sm) {
+    G = sm;
+    Yr = sm + 4 * fft8k::kPlaneG;
+    Yi = Yr + fft8k::kPlaneY;
+    tabf = Yi + fft8k::kPlaneY;
+    full = reinterpret_cast<uint64_t*>(tabf + fft8k::kTabFloats + 32);
+  }
+  __device__ __forceinline__ void init(const float* twiddles, int t) {
+    if (t == 0) {
+      mbar_init(&full[0], 1);
+      mbar_init(&full[1], 1);
+      fence_barrier_init();
+    }
+    for (int e = t; e < fft8k::kTabFloats; e += kFusedThreads) tabf[e] = twiddles[e];
+    __syncthreads();
+  }
+};
+// the four passes on buffer (gr, gi); `refill()` runs as soon as nobody reads the buffer any more
+template <bool INV, class Refill>
+__device__ __forceinline__ void fft8192_in_smem(float* gr, float* gi, const FftSmem& s, const fft8k::Tables& tb, int t,
+                                                Refill&& refill, float (&xr)[16], float (&xi)[16]) {
+  fft8k::p1<INV>(gr, gi, tb, t);
+  __syncthreads();
+  fft8k::p2<INV>(gr, gi, s.Yr, s.Yi, tb, t);
+  fence_proxy_async_smem();                        // pass-1 stores to G (generic proxy) before the bulk refill
+  __syncthreads();
+  refill();
+  fft8k::P3Regs q3;
+  fft8k::p3_load<INV>(s.Yr, s.Yi, t, q3);
+  __syncthreads();
+  fft8k::p3_store<INV>(s.Yr, s.Yi, tb, t, q3);
+  __syncthreads();
+  fft8k::p4<INV>(s.Yr, s.Yi, t, xr, xi);
+}
+
+// Xb[(il*I + i)*kNbA + f] = FFT of the window (x_left + i x_right)[(i-1) kB + m], m < kNbA  (zero outside [0, n)):
+// x_blocks_kernel + forward C2C in one kernel.  Requires n % 4 == 0 and 16-byte aligned rows (bulk copies).
+__global__ void __launch_bounds__(kFusedThreads, 1)
+x_fft_kernel(const float* __restrict__ x, float2* __restrict__ Xb, const float* __restrict__ twiddles, int64_t item0,
+             int I, int64_t n, int in_chs, int nblocks) {
+  extern __shared__ __align__(128) float sm[];
+  FftSmem s(sm);
+  const int t = threadIdx.x;
+  s.init(twiddles, t);
+  const fft8k::Tables tb = fft8k::carve_tables(s.tabf);
+  auto fetch = [&](int it, int m) {                // all threads: zero padding; thread 0: the bulk copies
+    if (m >= nblocks) return;
+    const int64_t il = m / I;
+    const int i = m - (int)il * I;
+    float* re = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    float* im = re + fft8k::kPlaneG;
+    const int64_t s0 = (int64_t)(i - 1) * kB;      // first sample of the window
+    const int lo = (i == 0) ? kB : 0;
+    const int64_t rem = n - s0;
+    const int hi = rem < kNbA ? (int)rem : kNbA;   // valid window samples are [lo, hi)
+    for (int e = t; e < lo; e += kFusedThreads) { re[e] = 0.f; im[e] = 0.f; }
+    for (int e = hi + t; e < kNbA; e += kFusedThreads) { re[e] = 0.f; im[e] = 0.f; }
+    if (t == 0) {
+      const float* xl = x + ((item0 + il) * in_chs) * n + s0;
+      const float* xr = in_chs == 1 ? xl : xl + n;
+      uint64_t* bar = &s.full[it & 1];
+      mbar_arrive_expect_tx(bar, 2u * (uint32_t)(hi - lo) * 4u);
+      for (int o = lo; o < hi; o += 4096) {
+        const uint32_t bytes = (uint32_t)((hi - o < 4096 ? hi - o : 4096) * 4);
+        tma_load_1d(re + o, xl + o, bytes, bar);
+        tma_load_1d(im + o, xr + o, bytes, bar);
+      }
+    }
+  };
+  fetch(0, blockIdx.x);
+  fetch(1, blockIdx.x + gridDim.x);
+  __syncthreads();                                 // the zero padding of the first two buffers is in place
+  int it = 0;
+  for (int m = blockIdx.x; m < nblocks; m += gridDim.x, ++it) {
+    mbar_wait(&s.full[it & 1], (uint32_t)((it >> 1) & 1));
+    float* gr = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    float xr[16], xi[16];
+    fft8192_in_smem<false>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2, m + 2 * gridDim.x); }, xr, xi);
+    float2* out = Xb + (int64_t)m * kNbA;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) out[t + 512 * q] = make_float2(xr[q], xi[q]);
+  }
+}
+
+// inverse C2C of the (planar) product spectra + mix_blocks_kernel in one kernel: block i of item il yields the wet
+// samples [i kB, (i+1) kB) as the second half of the transform; y = x + mix (wet - x).
+__global__ void __launch_bounds__(kFusedThreads, 1)
+ifft_mix_kernel(const float* __restrict__ Ypl, const float* __restrict__ twiddles, const float* __restrict__ x,
+                const float* __restrict__ params, float* __restrict__ y, float* __restrict__ wet_save, int64_t item0,
+                int I, int64_t n, int in_chs, int nblocks) {
+  extern __shared__ __align__(128) float sm[];
+  FftSmem s(sm);
+  const int t = threadIdx.x;
+  s.init(twiddles, t);
+  const fft8k::Tables tb = fft8k::carve_tables(s.tabf);
+  auto fetch = [&](int it, int m) {
+    if (t != 0 || m >= nblocks) return;
+    uint64_t* bar = &s.full[it & 1];
+    float* dst = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    const float* src = Ypl + (int64_t)m * 2 * kNbA;
+    mbar_arrive_expect_tx(bar, 2u * kNbA * 4u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tma_load_1d(dst + q * 4096, src + q * 4096, 16384u, bar);
+  };
+  fetch(0, blockIdx.x);
+  fetch(1, blockIdx.x + gridDim.x);
+  int it = 0;
+  for (int m = blockIdx.x; m < nblocks; m += gridDim.x, ++it) {
+    mbar_wait(&s.full[it & 1], (uint32_t)((it >> 1) & 1));
+    float* gr = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    float xr[16], xi[16];
+    fft8192_in_smem<true>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2, m + 2 * gridDim.x); }, xr, xi);
+    const int64_t il = m / I, b = item0 + il;
+    const int i = m - (int)il * I;
+    const float mix = params[b * 25 + 24];
+    const float* xl = x + (b * in_chs) * n;
+    const float* xrr = in_chs == 1 ? xl : xl + n;
+#pragma unroll
+    for (int q = 8; q < 16; ++q) {                 // outputs kB .. 2 kB - 1 of the transform
+      const int64_t tg = (int64_t)i * kB + (t + 512 * q - kB);
+      if (tg < n) {
+        const float a0 = xl[tg], a1 = xrr[tg];
+        y[(b * 2 + 0) * n + tg] = fmaf(mix, xr[q] - a0, a0);
+        y[(b * 2 + 1) * n + tg] = fmaf(mix, xi[q] - a1, a1);
+        if (wet_save) { wet_save[(b * 2 + 0) * n + tg] = xr[q]; wet_save[(b * 2 + 1) * n + tg] = xi[q]; }
+      }
+    }
   }
 }
 
@@ -750,7 +886,9 @@ __device__ __forceinline__ void cfma_conj(float2& acc, float2 p, float2 q) {    
 // A: [items][na][kNbA], Bm: [items][nbm][kNbA], Out: [items][nout][kNbA]; per channel, packed spectra.
 // grid = (ceil((kNbA/2+1)/128), items); thread = frequency pair (f, kNbA - f).  MAXB > 0: operands cached
 // in registers (na, nbm <= MAXB); MAXB == 0: generic loop straight from L2.
-template <int MAXB, bool CORR>
+// PLANAR: every output block is stored as [re plane kNbA][im plane kNbA] (what ifft_mix_kernel bulk-copies into the
+// shared-memory layout of fft8192.cuh) instead of (re, im) pairs (what cuFFT reads).
+template <int MAXB, bool CORR, bool PLANAR = false>
 __global__ void __launch_bounds__(128) partition_mac_kernel(const float2* __restrict__ A, const float2* __restrict__ Bm,
                                                             float2* __restrict__ Out, int na, int nbm, int nout,
                                                             float scale) {
@@ -763,8 +901,14 @@ __global__ void __launch_bounds__(128) partition_mac_kernel(const float2* __rest
   float2* out = Out + il * (int64_t)nout * kNbA;
   auto emit = [&](int o, float2 sl, float2 sr) {
     sl.x *= scale; sl.y *= scale; sr.x *= scale; sr.y *= scale;
-    out[(int64_t)o * kNbA + f] = make_float2(sl.x - sr.y, sl.y + sr.x);                 // L + i R
-    if (fm != f) out[(int64_t)o * kNbA + fm] = make_float2(sl.x + sr.y, sr.x - sl.y);   // conj(L) + i conj(R)
+    if (PLANAR) {
+      float* pl = reinterpret_cast<float*>(out + (int64_t)o * kNbA);
+      pl[f] = sl.x - sr.y; pl[kNbA + f] = sl.y + sr.x;
+      if (fm != f) { pl[fm] = sl.x + sr.y; pl[kNbA + fm] = sr.x - sl.y; }
+    } else {
+      out[(int64_t)o * kNbA + f] = make_float2(sl.x - sr.y, sl.y + sr.x);                 // L + i R
+      if (fm != f) out[(int64_t)o * kNbA + fm] = make_float2(sl.x + sr.y, sr.x - sl.y);   // conj(L) + i conj(R)
+    }
   };
   if constexpr (MAXB > 0) {
     float2 al[MAXB], ar[MAXB], bl[MAXB], br[MAXB];
@@ -1080,16 +1224,12 @@ int get_fft_tables(cudaStream_t st, const float** out) {
   *out = it->second;
   return DASP_OK;
 }
+int configure_fft_kernels();
 int launch_ifft_shape(float2* C, const float* tw, const float* params, float2* hs, bool save_f, int64_t items,
                       const Geom& g, int jb, cudaStream_t st) {
-  const size_t smem = sizeof(float) * kFusedSmemFloats + 2 * sizeof(uint64_t);
-  static std::map<int, bool> configured;             // per device, guarded by g_mu
-  int dev = 0;
-  DASP_CUDA_OK(cudaGetDevice(&dev));
-  if (!configured[dev]) {
-    DASP_CUDA_OK(cudaFuncSetAttribute(ifft_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[dev] = true;
-  }
+  int rc = configure_fft_kernels();
+  if (rc != DASP_OK) return rc;
+  const size_t smem = kFftSmemBytes;
   ifft_shape_kernel<<<dim3((unsigned)g.rpp, (unsigned)items), kFusedThreads, smem, st>>>(
       reinterpret_cast<float*>(C), tw, params, hs, save_f ? 1 : 0, (int)g.L, (int)g.leff, jb, (int)g.rpp);
   DASP_LAUNCH_OK("ifft_shape_kernel");
@@ -1181,14 +1321,28 @@ void bwd_layout(const Geom& g, size_t cufft_work, BwdWs& w) {
 }
 
 // out = conv / corr of packed block spectra, register-cached when both operands have <= 16 blocks
-template <bool CORR>
+template <bool CORR, bool PLANAR = false>
 void launch_mac(const float2* A, const float2* Bm, float2* Out, int na, int nbm, int nout, int64_t items, float scale,
                 cudaStream_t st) {
   dim3 grid((kNbA / 2 + 1 + 127) / 128, (unsigned)items);
   const int m = na > nbm ? na : nbm;
-  if (m <= 12)      partition_mac_kernel<12, CORR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
-  else if (m <= 16) partition_mac_kernel<16, CORR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
-  else              partition_mac_kernel<0, CORR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
+  if (m <= 12)      partition_mac_kernel<12, CORR, PLANAR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
+  else if (m <= 16) partition_mac_kernel<16, CORR, PLANAR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
+  else              partition_mac_kernel<0, CORR, PLANAR><<<grid, 128, 0, st>>>(A, Bm, Out, na, nbm, nout, scale);
+}
+
+// one-off opt-in to the large dynamic shared memory of the FFT kernels (per device, guarded by g_mu)
+int configure_fft_kernels() {
+  static std::map<int, bool> configured;
+  int dev = 0;
+  DASP_CUDA_OK(cudaGetDevice(&dev));
+  if (!configured[dev]) {
+    DASP_CUDA_OK(cudaFuncSetAttribute(ifft_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
+    DASP_CUDA_OK(cudaFuncSetAttribute(x_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
+    DASP_CUDA_OK(cudaFuncSetAttribute(ifft_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
+    configured[dev] = true;
+  }
+  return DASP_OK;
 }
 
 }  // namespace
@@ -1312,8 +1466,10 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     const bool own_fft = spectral && nb == fft8k::kN && g.L < (int64_t)1 << 31;
     if (own_fft && debug_reverb_path() == 2 && g.rpp <= kMaxFusedR) synth = 1;
     else if (own_fft && debug_reverb_path() != 1) synth = 2;
+    // audio convolution: block transforms on the own FFT (fused with their pre/post kernels) when the rows allow bulk copies
+    const bool own_conv = debug_reverb_path() != 1 && (n % 4 == 0) && aligned16(x);
     const float* tw = nullptr;
-    if (synth != 0 && (rc = get_fft_tables(st, &tw)) != DASP_OK) return rc;
+    if ((synth != 0 || own_conv) && (rc = get_fft_tables(st, &tw)) != DASP_OK) return rc;
     if (synth == 1) {
       if (dispatch_fused((int)g.rpp, H1, tw, params + item0 * 25, hs, f_save ? C : nullptr, item0, items, g.L, g.leff, J,
                          (unsigned long long)seed, st)) {
@@ -1355,11 +1511,24 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     }
 
     // ---- audio convolution (partitioned, frequency domain) ----
-    x_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(x, xs, item0, I, n, (int)in_chs);
-    DASP_LAUNCH_OK("x_blocks_kernel");
+    const int nblk = (int)(items * I);
+    const unsigned fft_grid = (unsigned)(nblk < sm_count() ? nblk : sm_count());
     DASP_CUFFT_OK(cufftSetStream(pl.hj_c2c.h, st));
     DASP_CUFFT_OK(cufftSetWorkArea(pl.hj_c2c.h, ws_cufft));
     DASP_CUFFT_OK(cufftExecC2C(pl.hj_c2c.h, (cufftComplex*)hs, (cufftComplex*)hs, CUFFT_FORWARD));
+    if (own_conv) {
+      if ((rc = configure_fft_kernels()) != DASP_OK) return rc;
+      x_fft_kernel<<<fft_grid, kFusedThreads, kFftSmemBytes, st>>>(x, xs, tw, item0, I, n, (int)in_chs, nblk);
+      DASP_LAUNCH_OK("x_fft_kernel");
+      launch_mac<false, true>(xs, hs, ws_ys, I, J, I, items, 1.0f / (float)kNbA, st);
+      DASP_LAUNCH_OK("partition_mac_kernel");
+      ifft_mix_kernel<<<fft_grid, kFusedThreads, kFftSmemBytes, st>>>(reinterpret_cast<const float*>(ws_ys), tw, x, params, y,
+                                                                     wet_save, item0, I, n, (int)in_chs, nblk);
+      DASP_LAUNCH_OK("ifft_mix_kernel");
+      continue;
+    }
+    x_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(x, xs, item0, I, n, (int)in_chs);
+    DASP_LAUNCH_OK("x_blocks_kernel");
     DASP_CUFFT_OK(cufftSetStream(pl.xi_c2c.h, st));
     DASP_CUFFT_OK(cufftSetWorkArea(pl.xi_c2c.h, ws_cufft));
     DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)xs, (cufftComplex*)xs, CUFFT_FORWARD));
