@@ -546,10 +546,12 @@ struct FftSmem {
     __syncthreads();
   }
 };
-// the four passes on buffer (gr, gi); `refill()` runs as soon as nobody reads the buffer any more
-template <bool INV, class Refill>
+// the four passes on buffer (gr, gi); `refill()` runs as soon as nobody reads the buffer any more, `early()` two
+// passes before the results exist (the place to issue global loads the epilogue needs, so that their latency is
+// covered by passes 3 and 4 -- with one lock-stepped CTA per SM nothing else would hide it)
+template <bool INV, class Refill, class Early>
 __device__ __forceinline__ void fft8192_in_smem(float* gr, float* gi, const FftSmem& s, const fft8k::Tables& tb, int t,
-                                                Refill&& refill, float (&xr)[16], float (&xi)[16]) {
+                                                Refill&& refill, Early&& early, float (&xr)[16], float (&xi)[16]) {
   fft8k::p1<INV>(gr, gi, tb, t);
   __syncthreads();
   fft8k::p2<INV>(gr, gi, s.Yr, s.Yi, tb, t);
@@ -559,6 +561,7 @@ __device__ __forceinline__ void fft8192_in_smem(float* gr, float* gi, const FftS
   fft8k::P3Regs q3;
   fft8k::p3_load<INV>(s.Yr, s.Yi, t, q3);
   __syncthreads();
+  early();
   fft8k::p3_store<INV>(s.Yr, s.Yi, tb, t, q3);
   __syncthreads();
   fft8k::p4<INV>(s.Yr, s.Yi, t, xr, xi);
@@ -606,7 +609,7 @@ x_fft_kernel(const float* __restrict__ x, float2* __restrict__ Xb, const float* 
     mbar_wait(&s.full[it & 1], (uint32_t)((it >> 1) & 1));
     float* gr = s.G + (it & 1) * 2 * fft8k::kPlaneG;
     float xr[16], xi[16];
-    fft8192_in_smem<false>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2, m + 2 * gridDim.x); }, xr, xi);
+    fft8192_in_smem<false>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2, m + 2 * gridDim.x); }, [] {}, xr, xi);
     float2* out = Xb + (int64_t)m * kNbA;
 #pragma unroll
     for (int q = 0; q < 16; ++q) out[t + 512 * q] = make_float2(xr[q], xi[q]);
@@ -640,19 +643,28 @@ ifft_mix_kernel(const float* __restrict__ Ypl, const float* __restrict__ twiddle
     mbar_wait(&s.full[it & 1], (uint32_t)((it >> 1) & 1));
     float* gr = s.G + (it & 1) * 2 * fft8k::kPlaneG;
     float xr[16], xi[16];
-    fft8192_in_smem<true>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2, m + 2 * gridDim.x); }, xr, xi);
     const int64_t il = m / I, b = item0 + il;
     const int i = m - (int)il * I;
     const float mix = params[b * 25 + 24];
     const float* xl = x + (b * in_chs) * n;
     const float* xrr = in_chs == 1 ? xl : xl + n;
+    float a0[8], a1[8];                            // the dry samples of this thread's 8 outputs
+    fft8192_in_smem<true>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2, m + 2 * gridDim.x); },
+                          [&] {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                              const int64_t tg = (int64_t)i * kB + (t + 512 * q);
+                              a0[q] = tg < n ? xl[tg] : 0.f;
+                              a1[q] = tg < n ? xrr[tg] : 0.f;
+                            }
+                          },
+                          xr, xi);
 #pragma unroll
     for (int q = 8; q < 16; ++q) {                 // outputs kB .. 2 kB - 1 of the transform
       const int64_t tg = (int64_t)i * kB + (t + 512 * q - kB);
       if (tg < n) {
-        const float a0 = xl[tg], a1 = xrr[tg];
-        y[(b * 2 + 0) * n + tg] = fmaf(mix, xr[q] - a0, a0);
-        y[(b * 2 + 1) * n + tg] = fmaf(mix, xi[q] - a1, a1);
+        y[(b * 2 + 0) * n + tg] = fmaf(mix, xr[q] - a0[q - 8], a0[q - 8]);
+        y[(b * 2 + 1) * n + tg] = fmaf(mix, xi[q] - a1[q - 8], a1[q - 8]);
         if (wet_save) { wet_save[(b * 2 + 0) * n + tg] = xr[q]; wet_save[(b * 2 + 1) * n + tg] = xi[q]; }
       }
     }
