@@ -378,8 +378,8 @@ def main():
                               "finish_dx_blocks_kernel, ir_grad_pp_kernel"}
         # DRAM bytes per item actually moved by the two reverb pipelines: dram__bytes_read.sum + dram__bytes_write.sum
         # summed over their kernels in one `ncu --set full` capture of a 128-item chunk at this geometry
-        # (profiles/r01_reverb_kernels_b128_full.md: fwd 1265 + 1434 MB, bwd 1636 + 359 MB per 128 items)
-        traffic_item = {"reverb_fwd": 21.09e6, "reverb_bwd": 15.59e6} if (N_SAMPLES, IR_LEN) == (48000, 96000) else {}
+        # (profiles/r01_reverb_kernels_b128_full.md: fwd 1110 + 1346 MB, bwd 1636 + 358 MB per 128 items)
+        traffic_item = {"reverb_fwd": 19.18e6, "reverb_bwd": 15.58e6} if (N_SAMPLES, IR_LEN) == (48000, 96000) else {}
         breakdown = {}
         for name, v in stages.items():
             m = statistics.mean(v)
