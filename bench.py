@@ -392,13 +392,14 @@ def main():
                         "unit": "GB/s", "frac": breakdown[dom]["frac"],
                         "traffic": traffic_item[dom] * bs if dom in traffic_item else None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": breakdown[dom]["ms"]}
-        chunks = -(-bs // F.REVERB_CHUNK_ITEMS)
+        chunk_items = F.reverb_chunk_items(dev)
+        chunks = -(-bs // chunk_items)
         own_launches_per_step = 1 + 2 + 1 + 1 + 1 + 2 + chunks * (5 + 6)   # eq f/b, comp f/b, dist f/b, reverb per chunk
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": make_config(bs, world, F.REVERB_CHUNK_ITEMS),
+            "config": make_config(bs, world, chunk_items),
             "roofline": roofline, "stages": breakdown,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": own_launches_per_step * args.steps, "clocks": clocks,

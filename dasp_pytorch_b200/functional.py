@@ -525,9 +525,18 @@ def parametric_eq_packed(x: torch.Tensor, sample_rate: float, params: torch.Tens
 
 import os as _os
 
-# items per pass of the reverb pipeline (bounds the workspace; measured on B200: 8 -> 55 ms, 16 -> 42 ms,
-# 32 -> 34 ms per chain step at batch 1024 (first pipeline); 128 is the default since the partitioned rewrite; override for experiments with DASP_REVERB_CHUNK)
-REVERB_CHUNK_ITEMS = int(_os.environ.get("DASP_REVERB_CHUNK", "128"))
+# Items per pass of the reverb pipeline (bounds the workspace).  Default: one item per SM of the device, so that the
+# one-CTA-per-SM FFT kernels run in whole waves (ifft_shape_kernel: R CTAs per item -> exactly R waves; the persistent
+# block-transform kernels: the same number of blocks per CTA).  Measured on B200 (148 SMs), chain step at batch 1024:
+# 74 -> 14.83 ms, 128 -> 14.61 ms, 148 -> 14.11 ms.  Override for experiments with DASP_REVERB_CHUNK.
+REVERB_CHUNK_ITEMS = int(_os.environ.get("DASP_REVERB_CHUNK", "0"))      # 0 = automatic
+
+
+def reverb_chunk_items(device) -> int:
+    """Items per pass of the reverb pipeline on ``device`` (see REVERB_CHUNK_ITEMS)."""
+    if REVERB_CHUNK_ITEMS > 0:
+        return REVERB_CHUNK_ITEMS
+    return int(torch.cuda.get_device_properties(device).multi_processor_count)
 
 
 class _ReverbFn(torch.autograd.Function):
@@ -647,7 +656,7 @@ def noise_shaped_reverberation(
     else:
         seed = int(torch.empty((), dtype=torch.int64).random_().item())
     y = _ReverbFn.apply(xf, packed, noise, seed, sample_rate, int(num_samples), int(num_bandpass_taps),
-                        REVERB_CHUNK_ITEMS)
+                        reverb_chunk_items(xf.device))
     return y.to(dt)
 
 
@@ -667,5 +676,6 @@ def noise_shaped_reverberation_packed(x: torch.Tensor, sample_rate: float, param
         noise = noise.to(device=xf.device, dtype=torch.float32).contiguous()
     else:
         seed = int(torch.empty((), dtype=torch.int64).random_().item())
-    y = _ReverbFn.apply(xf, packed, noise, seed, sample_rate, int(num_samples), int(num_bandpass_taps), REVERB_CHUNK_ITEMS)
+    y = _ReverbFn.apply(xf, packed, noise, seed, sample_rate, int(num_samples), int(num_bandpass_taps),
+                        reverb_chunk_items(xf.device))
     return y.to(dt)

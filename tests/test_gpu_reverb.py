@@ -219,3 +219,29 @@ def test_reverb_ir_synthesis_variants_agree(cuda_device, n, L):
         assert peak_err(y, y_ref).max() < 2e-5, (path, peak_err(y, y_ref))
         assert peak_err(dx, dx_ref).max() < 2e-5, (path, peak_err(dx, dx_ref))
         assert float((dp - dp_ref).abs().max() / dp_ref.abs().max()) < 2e-5, path
+
+
+def test_reverb_chunking_is_invisible(cuda_device, monkeypatch):
+    """The pipeline processes the batch in chunks (default: one item per SM); the Philox stream is keyed by the
+    absolute item index, so any chunk size -- including one that leaves a remainder chunk -- gives the same result."""
+    import dasp_pytorch_b200 as D
+    from dasp_pytorch_b200 import functional as F
+    bs, n, L, taps = 5, 8000, 12000, 255
+    g = torch.Generator().manual_seed(3)
+    x = (torch.rand(bs, 2, n, generator=g) * 2 - 1).to(cuda_device)
+    p = [q.to(cuda_device) for q in _params01(bs, 8)]
+
+    def run(chunk):
+        monkeypatch.setattr(F, "REVERB_CHUNK_ITEMS", chunk)
+        torch.manual_seed(5)
+        xx = x.clone().requires_grad_(True)
+        pp = [q.clone().requires_grad_(True) for q in p]
+        y = D.noise_shaped_reverberation(xx, SR, *pp, num_samples=L, num_bandpass_taps=taps)
+        y.square().sum().backward()
+        return y.detach(), xx.grad, torch.stack([q.grad for q in pp], 1)
+
+    ref = run(0)                                    # automatic: the whole batch in one chunk
+    for chunk in (1, 2, 3):
+        got = run(chunk)
+        for a, b in zip(got, ref):              # (cuFFT may pick another kernel for another batch size: rounding only)
+            assert float((a - b).abs().max() / b.abs().max()) < 2e-6, chunk
