@@ -13,13 +13,15 @@
 //     (y[n] = sum_{t<=n} IR[t] x[n-t], n < N), so only those are synthesised -- an exact saving.
 //   * The LEFT and RIGHT channel of a band / of the audio are packed as real/imag of one complex sequence.
 //   * IR synthesis, device noise (default): spectral_gen_kernel draws the FILTERED noise spectrum directly
-//     (Philox4x32-10 + Box-Muller; see the comment at the kernel), one inverse C2C, shape_ir_pp_kernel
-//     (envelope * gain * band mean -> IR written straight into the partition layout of the convolution).
+//     (Philox4x32-10 + Box-Muller; see the comment at the kernel); ifft_shape_kernel = own in-shared-memory inverse
+//     FFT (fft8192.cuh) fused with envelope * gain * band mean -> IR written straight into the partition layout of
+//     the convolution.  (Test-hook variants: batched cuFFT + shape_ir_pp_kernel, and one cluster kernel per item.)
 //   * IR synthesis, parity mode (caller's noise tensor): overlap-save blocks -> C2C -> cmul_filter_pairs ->
 //     inverse C2C -> shape_ir_pairs_kernel.
-//   * Audio convolution: uniformly partitioned overlap-save in the frequency domain (x_blocks_kernel, C2C,
-//     partition_mac_kernel, inverse C2C, mix_blocks_kernel).
-//   * Items are processed in chunks (128 by default) to bound the workspace.
+//   * Audio convolution: uniformly partitioned overlap-save in the frequency domain: x_fft_kernel (window gather +
+//     FFT), partition_mac_kernel, ifft_mix_kernel (inverse FFT + crop + wet/dry mix), all on the own FFT; rows that
+//     are not 16-byte aligned use x_blocks_kernel, cuFFT C2C, mix_blocks_kernel.
+//   * Items are processed in chunks (chosen by the caller; the Python host uses one item per SM) to bound the workspace.
 //
 // Backward (A.5): g_blocks_kernel (+ dL/dmix partials), C2C, two correlation passes of partition_mac_kernel
 // against the saved block spectra (dL/dx windows, dL/dIR partitions), two inverse C2C, finish_dx_blocks_kernel,
