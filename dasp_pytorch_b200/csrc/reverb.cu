@@ -315,9 +315,13 @@ __device__ __forceinline__ void spectral_unit(int j1, int nb, const float2* __re
     const float2 r = c_root[R][m];
     rx[m] = make_float2(r.x, r.x); ry[m] = make_float2(r.y, r.y); nry[m] = make_float2(-r.y, -r.y);
   }
+  // per-class twiddle steps e^{2 pi i j1 / n1} and e^{2 pi i (nb - j1) / n1} = e^{2 pi i / R} conj(the former)
   float2 w1a, w1b;
   sincospif(2.0f * (float)j1 / (float)n1, &w1a.y, &w1a.x);
-  sincospif(2.0f * (float)(nb - j1) / (float)n1, &w1b.y, &w1b.x);
+  {
+    const float2 r1 = (R == 1) ? make_float2(1.f, 0.f) : c_root[R][1 % R];
+    w1b = make_float2(fmaf(r1.x, w1a.x, r1.y * w1a.y), fmaf(r1.y, w1a.x, -r1.x * w1a.y));
+  }
   const float2 wx = make_float2(w1a.x, w1b.x), wy = make_float2(w1a.y, w1b.y), nwy = make_float2(-w1a.y, -w1b.y);
   float2 tx = make_float2(1.f, 1.f), ty = make_float2(0.f, 0.f);      // twiddle e^{2 pi i j b / n1}, both classes
 #pragma unroll
@@ -506,12 +510,20 @@ ifft_shape_kernel(float* __restrict__ Cpl, const float* __restrict__ twiddles, c
     __syncthreads();
     float xr[16], xi[16];
     fft8k::p4<true>(Yr, Yi, t, xr, xi);
+    float e_prev = 0.f;
     const float g = gk[k], rr = rk[k];
     float2* fout = reinterpret_cast<float2*>(blk + k * band_stride);
+    // envelope gain_k exp(rr tt(tau)) at the thread's taps tau_q = R (t + 512 q) + c: evaluated at every 4th tap,
+    // the three taps in between follow by the constant ratio exp(rr step 512 R) (tt is linear in tau up to fp32
+    // rounding of the linspace, so this stays within ~1e-6 of the per-tap evaluation)
+    const float rho = __expf(rr * step * (float)(512 * R));
 #pragma unroll
     for (int q = 0; q < 16; ++q) {
       const int a = t + 512 * q;
-      const float e = g * __expf(rr * time_axis32(R * a + c, L, step));
+      float e;
+      if ((q & 3) == 0) e = g * __expf(rr * time_axis32(R * a + c, L, step));
+      else e = e_prev * rho;
+      e_prev = e;
       accr[q] = fmaf(e, xr[q], accr[q]);
       acci[q] = fmaf(e, xi[q], acci[q]);
       if (save_f) fout[a] = make_float2(xr[q], xi[q]);
