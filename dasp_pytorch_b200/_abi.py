@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DASP_LIB_PATH") or os.path.join(_HERE, "libdasp_b200.so")   # override: experiments only
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class DaspError(RuntimeError):
@@ -43,6 +43,8 @@ _SIGNATURES = {
     "dasp_debug_force_warps": (None, [c_int]),
     "dasp_debug_reverb_path": (None, [c_int]),
     "dasp_debug_reverb_last_path": (c_int, []),
+    "dasp_debug_reverb_flat_filterbank": (None, [c_int]),
+    "dasp_denormalize": (c_int, [P, P, P, P, P, I64, I64, P]),
     "dasp_gain_fwd": (c_int, [P, P, P, I64, I64, I64, P]),
     "dasp_gain_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "dasp_distortion_fwd": (c_int, [P, P, P, I64, I64, P]),
@@ -60,7 +62,7 @@ _SIGNATURES = {
     "dasp_eq_fwd": (c_int, [P, P, P, P, I64, I64, I64, c_float, P]),
     "dasp_eq_bwd": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),
     "dasp_reverb_geometry": (c_int, [I64, I64, I64, I64, I64, ctypes.POINTER(ReverbGeom)]),
-    "dasp_reverb_fwd": (c_int, [P, I64, P, P, c_uint64, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, c_float, P]),
+    "dasp_reverb_fwd": (c_int, [P, I64, P, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, c_float, P]),
     "dasp_reverb_bwd": (c_int, [P, P, I64, P, P, P, P, P, P, P, P, I64, I64, I64, I64, I64, I64, I64, P]),
     "dasp_reverb_filterbank": (c_int, [I64, c_double, ctypes.POINTER(c_float)]),
     "dasp_dynamics_tile_len": (I64, [I64, I64]),

@@ -61,6 +61,10 @@ int debug_forced_warps();
 // Test hook (dasp_debug_reverb_path): IR synthesis of the device-noise reverb: 0 = automatic, 1 = generator / cuFFT /
 // shaping kernels, 2 = single cluster kernel
 int debug_reverb_path();
+// Test hook (dasp_debug_reverb_flat_filterbank): the spectral IR synthesis uses unit-impulse "filters", so the
+// band-filtered noise it keeps for the backward IS the periodic white sequence w_k the generator draws; the parity
+// test rebuilds the reference-style noise tensor from it and checks the default path against the oracle.
+int debug_flat_filterbank();
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__

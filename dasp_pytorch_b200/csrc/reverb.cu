@@ -196,7 +196,7 @@ __global__ void noise_pairs_layout_kernel(const float* __restrict__ noise, float
 // addressed by its absolute sample position, so the overlapping part of consecutive blocks is simply
 // generated twice and nothing depends on the chunking.
 __global__ void noise_pairs_philox_kernel(float2* __restrict__ C, int64_t item0, int nbk, int nb, int hop,
-                                          unsigned long long seed) {
+                                          const unsigned long long* seed) {
   const int b = blockIdx.x, k = blockIdx.y;
   const int64_t il = blockIdx.z;
   const unsigned long long sig_l = (unsigned long long)(((item0 + il) * 2 + 0) * kBands + k);
@@ -205,8 +205,8 @@ __global__ void noise_pairs_philox_kernel(float2* __restrict__ C, int64_t item0,
   for (int q4 = threadIdx.x; q4 < nb / 4; q4 += blockDim.x) {
     const unsigned long long quad = (unsigned long long)(((int64_t)b * hop) / 4 + q4);   // hop % 4 == 0
     curandStatePhilox4_32_10_t sl, sr;
-    curand_init(seed, (sig_l << 24) + quad, 0ull, &sl);
-    curand_init(seed, (sig_r << 24) + quad, 0ull, &sr);
+    curand_init(__ldg(seed), (sig_l << 24) + quad, 0ull, &sl);
+    curand_init(__ldg(seed), (sig_r << 24) + quad, 0ull, &sr);
     const float4 l = curand_normal4(&sl), r = curand_normal4(&sr);
     out[q4 * 2 + 0] = make_float4(l.x, r.x, l.y, r.y);
     out[q4 * 2 + 1] = make_float4(l.z, r.z, l.w, r.w);
@@ -239,9 +239,9 @@ __global__ void cmul_filter_pairs_kernel(float2* __restrict__ C, const float2* _
 // Philox4x32-10 (Salmon et al., SC'11), counter = (c0, c1, c2, c3), key = (k0, k1); written out instead of the
 // cuRAND state machinery because this kernel needs exactly one block of 4 words per call site
 struct PhiloxKeys { uint2 k[10]; };           // the ten round keys (key + r * Weyl constants): one schedule per thread
-__device__ __forceinline__ PhiloxKeys philox_keys(unsigned long long seed) {
+__device__ __forceinline__ PhiloxKeys philox_keys(unsigned long long sd) {
   PhiloxKeys ks;
-  uint2 k = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+  uint2 k = make_uint2((unsigned)sd, (unsigned)(sd >> 32));
 #pragma unroll
   for (int r = 0; r < 10; ++r) { ks.k[r] = k; k.x += 0x9E3779B9u; k.y += 0xBB67AE85u; }
   return ks;
@@ -347,13 +347,13 @@ __device__ __forceinline__ void spectral_unit(int j1, int nb, const float2* __re
 //                  layout of fft8192.cuh, so ifft_shape_kernel can fetch a class with plain bulk copies.
 template <int R, bool PLANAR>
 __global__ void spectral_gen_kernel(float2* __restrict__ C, const float2* __restrict__ H1, int64_t item0, int nb,
-                                    unsigned long long seed) {
+                                    const unsigned long long* seed) {
   const int j1 = blockIdx.x * blockDim.x + threadIdx.x;       // residue class 0 .. nb/2
   if (j1 > nb / 2) return;
   const int k = blockIdx.y;
   const int64_t il = blockIdx.z;
   const unsigned long long pair = (unsigned long long)((item0 + il) * kBands + k);
-  const PhiloxKeys keys = philox_keys(seed);
+  const PhiloxKeys keys = philox_keys(__ldg(seed));
   const bool self_mirror = (j1 == 0) || (2 * j1 == nb);     // class nb - j1 is class j1 itself
   float2* outp = C + ((il * kBands + k) * R) * (int64_t)nb;
   spectral_unit<R>(j1, nb, H1 + (int64_t)k * (R * nb / 2 + 1), pair, keys, [&](int b, float2 q, float2 qm) {
@@ -720,7 +720,7 @@ template <int R>
 __global__ void __launch_bounds__(kFusedThreads, 1)
 ir_synth_fused_kernel(const float2* __restrict__ H1, const float* __restrict__ twiddles,
                       const float* __restrict__ params, float2* __restrict__ Hb, float2* __restrict__ Csave, int64_t item0, int64_t L, int64_t leff, int jb,
-                      unsigned long long seed) {
+                      const unsigned long long* seed) {
   constexpr int nb = fft8k::kN, U = nb / 2 + 1, CT = R * kFusedThreads, total = kBands * U;
   static_assert(CT < U, "at most one band may complete per generation round");
   extern __shared__ __align__(16) float sm[];
@@ -743,7 +743,7 @@ ir_synth_fused_kernel(const float2* __restrict__ H1, const float* __restrict__ t
   float* remote[R];                                // G of every CTA of the cluster
 #pragma unroll
   for (int b = 0; b < R; ++b) remote[b] = map_to_cta(G, (unsigned)b);
-  const PhiloxKeys keys = philox_keys(seed);
+  const PhiloxKeys keys = philox_keys(__ldg(seed));
   const float step = 1.0f / (float)(L - 1);
   float accr[16], acci[16];
 #pragma unroll
@@ -1162,7 +1162,8 @@ int get_filterbank_n1(const Geom& g, double sr, cudaStream_t st, const float2** 
   int dev = 0;
   DASP_CUDA_OK(cudaGetDevice(&dev));
   const int64_t n1 = g.n1(), n1c = g.n1c();
-  FbKey key{dev, g.taps, -n1, sr};
+  const bool flat = debug_flat_filterbank();        // test hook: H_k = 1 -> f_k is the white periodic sequence itself
+  FbKey key{dev, flat ? -g.taps : g.taps, -n1, sr};
   auto it = g_fb.find(key);
   if (it != g_fb.end()) { *out = reinterpret_cast<const float2*>(it->second); return DASP_OK; }
   DASP_REQUIRE(sr / 2.0 > 18000.0, "sample_rate %.1f too low: the filter bank needs 18 kHz < sr/2 (signal.py:84)", sr);
@@ -1178,6 +1179,10 @@ int get_filterbank_n1(const Geom& g, double sr, cudaStream_t st, const float2** 
   }
   std::vector<float> taps;
   octave_filterbank((int)g.taps, sr, taps);
+  if (flat) {
+    taps.assign(taps.size(), 0.f);
+    for (int k = 0; k < kBands; ++k) taps[(size_t)k * g.taps] = 1.0f;      // unit impulse at lag 0
+  }
   std::vector<float> padded((size_t)kBands * n1, 0.f);
   const float inv = 1.0f / (float)n1;
   for (int k = 0; k < kBands; ++k)
@@ -1204,7 +1209,7 @@ int get_filterbank_n1(const Geom& g, double sr, cudaStream_t st, const float2** 
 }
 
 template <int R>
-void launch_spectral(float2* C, const float2* H1, int64_t item0, int64_t items, int nb, unsigned long long seed,
+void launch_spectral(float2* C, const float2* H1, int64_t item0, int64_t items, int nb, const unsigned long long* seed,
                      bool planar, cudaStream_t st) {
   const int threads = 128;
   dim3 grid((unsigned)((nb / 2 + 1 + threads - 1) / threads), kBands, (unsigned)items);
@@ -1212,7 +1217,7 @@ void launch_spectral(float2* C, const float2* H1, int64_t item0, int64_t items, 
   else        spectral_gen_kernel<R, false><<<grid, threads, 0, st>>>(C, H1, item0, nb, seed);
 }
 bool dispatch_spectral(int R, float2* C, const float2* H1, int64_t item0, int64_t items, int nb,
-                       unsigned long long seed, bool planar, cudaStream_t st) {
+                       const unsigned long long* seed, bool planar, cudaStream_t st) {
   switch (R) {
 #define DASP_R(r) case r: launch_spectral<r>(C, H1, item0, items, nb, seed, planar, st); return true;
     DASP_R(1) DASP_R(2) DASP_R(3) DASP_R(4) DASP_R(5) DASP_R(6) DASP_R(7) DASP_R(8) DASP_R(9) DASP_R(10)
@@ -1265,7 +1270,7 @@ int g_last_fused = 0;                                // test hook: IR-synthesis 
 std::map<std::pair<int, int>, int> g_fused_ok;      // (device, R) -> clusters that fit, guarded by g_mu
 template <int R>
 bool launch_fused(const float2* H1, const float* tw, const float* params, float2* hs, float2* Csave, int64_t item0, int64_t items,
-                  int64_t L, int64_t leff, int jb, unsigned long long seed, cudaStream_t st) {
+                  int64_t L, int64_t leff, int jb, const unsigned long long* seed, cudaStream_t st) {
   auto kern = ir_synth_fused_kernel<R>;
   const size_t smem = sizeof(float) * kFusedSmemFloats;
   cudaLaunchConfig_t cfg = {};
@@ -1295,7 +1300,7 @@ bool launch_fused(const float2* H1, const float* tw, const float* params, float2
   return true;
 }
 bool dispatch_fused(int R, const float2* H1, const float* tw, const float* params, float2* hs, float2* Csave, int64_t item0,
-                    int64_t items, int64_t L, int64_t leff, int jb, unsigned long long seed, cudaStream_t st) {
+                    int64_t items, int64_t L, int64_t leff, int jb, const unsigned long long* seed, cudaStream_t st) {
   switch (R) {
 #define DASP_R(r) case r: return launch_fused<r>(H1, tw, params, hs, Csave, item0, items, L, leff, jb, seed, st);
     DASP_R(1) DASP_R(2) DASP_R(3) DASP_R(4) DASP_R(5) DASP_R(6) DASP_R(7) DASP_R(8)
@@ -1441,7 +1446,7 @@ int dasp_reverb_geometry(int64_t bs, int64_t n, int64_t num_samples, int64_t tap
   return DASP_OK;
 }
 
-int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const float* noise, uint64_t seed, float* y,
+int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const float* noise, const uint64_t* seed_dev, float* y,
                     float* wet_save, float* f_save, void* xspec_save, void* irspec_save, void* workspace,
                     int64_t workspace_bytes, int64_t bs, int64_t n, int64_t num_samples, int64_t taps,
                     int64_t chunk_items, float sample_rate, void* stream) {
@@ -1451,6 +1456,8 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
   DASP_REQUIRE(in_chs == 1 || in_chs == 2, "only mono/stereo signals are supported");
   if (bs == 0) return DASP_OK;
   DASP_REQUIRE(x && params && y && workspace, "reverb fwd: null pointer");
+  DASP_REQUIRE(noise != nullptr || seed_dev != nullptr, "reverb fwd: device-noise mode needs seed_dev (a device pointer)");
+  const unsigned long long* seed = reinterpret_cast<const unsigned long long*>(seed_dev);
   cudaStream_t st = (cudaStream_t)stream;
   std::lock_guard<std::mutex> lk(g_mu);
   const float2 *H = nullptr, *H1 = nullptr;
@@ -1498,7 +1505,7 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     if ((synth != 0 || own_conv) && (rc = get_fft_tables(st, &tw)) != DASP_OK) return rc;
     if (synth == 1) {
       if (dispatch_fused((int)g.rpp, H1, tw, params + item0 * 25, hs, f_save ? C : nullptr, item0, items, g.L, g.leff, J,
-                         (unsigned long long)seed, st)) {
+                         seed, st)) {
         DASP_LAUNCH_OK("ir_synth_fused_kernel");
       } else {
         synth = 2;                                   // the device cannot co-schedule such a cluster
@@ -1507,12 +1514,12 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     g_last_fused = synth;
     if (synth == 1) {
     } else if (synth == 2) {
-      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, (unsigned long long)seed, /*planar=*/true, st);
+      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, seed, /*planar=*/true, st);
       DASP_LAUNCH_OK("spectral_gen_kernel");
       if ((rc = launch_ifft_shape(C, tw, params + item0 * 25, hs, f_save != nullptr, items, g, J, st)) != DASP_OK) return rc;
     } else if (spectral) {
       // device noise: draw the filtered spectrum directly, one inverse transform (polyphase layout)
-      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, (unsigned long long)seed, /*planar=*/false, st);
+      dispatch_spectral((int)g.rpp, C, H1, item0, items, nb, seed, /*planar=*/false, st);
       DASP_LAUNCH_OK("spectral_gen_kernel");
       DASP_CUFFT_OK(cufftSetStream(pl.pp_c2c.h, st));
       DASP_CUFFT_OK(cufftSetWorkArea(pl.pp_c2c.h, ws_cufft));
@@ -1523,7 +1530,7 @@ int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const f
     } else {
       // parity mode (caller's noise tensor) or very long IR: time-domain noise, overlap-save blocks
       if (noise) noise_pairs_layout_kernel<<<gblk, 256, 0, st>>>(noise, C, item0, nbk, nb, hop, lp);
-      else       noise_pairs_philox_kernel<<<gblk, 256, 0, st>>>(C, item0, nbk, nb, hop, (unsigned long long)seed);
+      else       noise_pairs_philox_kernel<<<gblk, 256, 0, st>>>(C, item0, nbk, nb, hop, seed);
       DASP_LAUNCH_OK("reverb noise kernel");
       DASP_CUFFT_OK(cufftSetStream(pl.blk_c2c.h, st));
       DASP_CUFFT_OK(cufftSetWorkArea(pl.blk_c2c.h, ws_cufft));

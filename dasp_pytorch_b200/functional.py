@@ -539,6 +539,22 @@ def reverb_chunk_items(device) -> int:
     return int(torch.cuda.get_device_properties(device).multi_processor_count)
 
 
+def _noise_or_seed(noise, xf, bs, num_samples, num_bandpass_taps):
+    """parity mode: validate the caller's noise tensor; default mode: draw the 64-bit Philox key ON THE DEVICE.
+
+    The reference draws its noise with ``torch.randn`` (``functional.py:547-548``), which is reproducible under
+    ``torch.manual_seed`` and, on CUDA, graph-safe (fresh values on every replay of a captured graph).  The key of
+    the in-kernel generator is therefore one ``random_()`` word of torch's CUDA generator, left in device memory
+    and read by the kernels when they run: no host round trip, same reproducibility, and a captured graph
+    re-draws it on every replay (torch registers the generator's Philox offset with the graph)."""
+    if noise is not None:
+        expect = (bs * 2, 12, num_samples + num_bandpass_taps - 1)
+        if tuple(noise.shape) != expect:
+            raise ValueError(f"noise must have shape {expect}, got {tuple(noise.shape)}")
+        return noise.to(device=xf.device, dtype=torch.float32).contiguous(), None
+    return None, torch.empty(1, dtype=torch.int64, device=xf.device).random_()
+
+
 class _ReverbFn(torch.autograd.Function):
     """x (bs, 1|2, n), params (bs, 25) -> y (bs, 2, n)."""
 
@@ -560,7 +576,7 @@ class _ReverbFn(torch.autograd.Function):
                 xspec = torch.empty(geom.xspec_c64, dtype=torch.complex64, device=dev)
                 irspec = torch.empty(geom.irspec_c64, dtype=torch.complex64, device=dev)
             with _timed("reverb_fwd", dev):
-                check(lib.dasp_reverb_fwd(ptr(x), in_chs, ptr(params), ptr(noise), int(seed), ptr(y), ptr(wet),
+                check(lib.dasp_reverb_fwd(ptr(x), in_chs, ptr(params), ptr(noise), ptr(seed), ptr(y), ptr(wet),
                                           ptr(fsave), ptr(xspec), ptr(irspec), ptr(ws), ws.numel(), bs, n, num_samples,
                                           taps, chunk, float(sample_rate), stream_ptr(dev)), "dasp_reverb_fwd")
         if need_bwd:
@@ -631,8 +647,9 @@ def noise_shaped_reverberation(
     ``torch.randn(bs*2, 12, num_samples + num_bandpass_taps - 1)`` inside the call
     (``functional.py:547-548``).  Pass that tensor here to reproduce a seeded reference call
     exactly (parity tests); by default fresh N(0,1) noise is generated on the device with
-    Philox4x32-10, keyed by a seed taken from the default torch CPU generator (so
-    ``torch.manual_seed`` makes the call reproducible).
+    Philox4x32-10, keyed by one 64-bit word drawn from torch's CUDA generator and kept in device
+    memory (``torch.manual_seed`` makes the call reproducible; a captured CUDA graph draws fresh
+    noise on every replay, like the reference's ``torch.randn`` would).
     """
     assert num_bandpass_taps % 2 == 1, "num_bandpass_taps must be odd"
     xf, dt = _audio(x)
@@ -647,14 +664,7 @@ def noise_shaped_reverberation(
     )
     packed = torch.stack([_param(p, bs, xf, f"noise_shaped_reverberation parameter {i}", allow_broadcast=True)
                           for i, p in enumerate(plist)], dim=1).contiguous()
-    seed = 0
-    if noise is not None:
-        expect = (bs * 2, 12, num_samples + num_bandpass_taps - 1)
-        if tuple(noise.shape) != expect:
-            raise ValueError(f"noise must have shape {expect}, got {tuple(noise.shape)}")
-        noise = noise.to(device=xf.device, dtype=torch.float32).contiguous()
-    else:
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    noise, seed = _noise_or_seed(noise, xf, bs, num_samples, num_bandpass_taps)
     y = _ReverbFn.apply(xf, packed, noise, seed, sample_rate, int(num_samples), int(num_bandpass_taps),
                         reverb_chunk_items(xf.device))
     return y.to(dt)
@@ -668,14 +678,7 @@ def noise_shaped_reverberation_packed(x: torch.Tensor, sample_rate: float, param
     bs, chs, _ = xf.shape
     assert chs <= 2, "only mono/stereo signals are supported"
     packed = _packed(params, bs, 25, xf, "params")
-    seed = 0
-    if noise is not None:
-        expect = (bs * 2, 12, num_samples + num_bandpass_taps - 1)
-        if tuple(noise.shape) != expect:
-            raise ValueError(f"noise must have shape {expect}, got {tuple(noise.shape)}")
-        noise = noise.to(device=xf.device, dtype=torch.float32).contiguous()
-    else:
-        seed = int(torch.empty((), dtype=torch.int64).random_().item())
+    noise, seed = _noise_or_seed(noise, xf, bs, num_samples, num_bandpass_taps)
     y = _ReverbFn.apply(xf, packed, noise, seed, sample_rate, int(num_samples), int(num_bandpass_taps),
                         reverb_chunk_items(xf.device))
     return y.to(dt)

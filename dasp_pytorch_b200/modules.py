@@ -9,10 +9,15 @@ drop-in contract.  ``process(x, *args)`` forwards positionally (``modules.py:53-
 
 Differences, all on the host side:
   * the range check of ``denormalize_param_dict`` (reference ``modules.py:83-84``) costs the reference two
-    device->host synchronisations per parameter; here it is ONE fused check per call;
-  * ``Distortion`` takes a ``sample_rate`` and uses the functional's real keyword ``drive_db``: the reference
-    class cannot be called through ``process_normalized`` at all (it has no ``sample_rate`` attribute and
-    names its parameter ``gain_db``).
+    device->host synchronisations per parameter.  Here the packed path runs ONE kernel (``dasp_denormalize``)
+    that maps the whole ``(batch, P)`` tensor and checks the range on the device: an offending value becomes
+    NaN and raises a device flag.  Outside CUDA-graph capture the flag is read back once per call and the
+    reference's ``ValueError`` (with the parameter name) is raised; under capture nothing is read back -- the
+    flag stays on the device (``Processor.range_violation()``) and the NaN makes the offending item visible;
+  * ``Distortion`` keeps the reference's positional order ``(min_gain_db, max_gain_db)`` and takes
+    ``sample_rate`` as a trailing keyword; its parameter is keyed by the functional's real keyword ``drive_db``
+    (the reference's key ``gain_db`` cannot be dispatched by name to ``distortion(x, sr, drive_db)`` --
+    SURVEY.md fact 8); ``param_ranges["gain_db"]`` still resolves, as an alias.
 """
 from __future__ import annotations
 
@@ -39,16 +44,60 @@ def normalize(val, min_val, max_val):
     return (val - min_val) / (max_val - min_val)
 
 
+class _DenormFn(torch.autograd.Function):
+    """(bs, P) in [0, 1] -> physical units, one kernel (``dasp_denormalize``); gradient = g * span."""
+
+    @staticmethod
+    def forward(ctx, p01, lo, span, flag):
+        from dasp_pytorch_b200 import _abi
+        p = p01.to(torch.float32).contiguous()
+        out = torch.empty_like(p)
+        with torch.cuda.device(p.device):
+            _abi.check(_abi.lib().dasp_denormalize(_abi.ptr(p), _abi.ptr(lo), _abi.ptr(span), _abi.ptr(out),
+                                                   _abi.ptr(flag), p.shape[0], p.shape[1],
+                                                   _abi.stream_ptr(p.device)), "dasp_denormalize")
+        ctx.save_for_backward(span)
+        ctx.in_dtype = p01.dtype
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (span,) = ctx.saved_tensors
+        return (g * span).to(ctx.in_dtype), None, None, None
+
+
+class _RangeDict(dict):
+    """``param_ranges`` with read-only aliases (reference key names that differ from the functional keyword)."""
+
+    def __init__(self, *a, aliases=None, **kw):
+        super().__init__(*a, **kw)
+        self._aliases = dict(aliases or {})
+
+    def __missing__(self, key):
+        if key in self._aliases:
+            return self[self._aliases[key]]
+        raise KeyError(key)
+
+
 class Processor:
     """Base class: subclasses set ``sample_rate``, ``process_fn`` and ``param_ranges``."""
 
     sample_rate = None
     process_fn = None
     param_ranges: Dict[str, tuple] = {}
+    # True (default): outside CUDA-graph capture an out-of-range parameter raises ValueError like the reference
+    # (one device->host read per call).  False: never read back; use range_violation() when convenient.
+    strict_range_check = True
 
+    # Plain attribute like the reference (its subclasses assign ``self.num_params = len(self.param_ranges)``);
+    # processors that never assign it get the length of their ranges.
     @property
     def num_params(self) -> int:
-        return len(self.param_ranges)
+        return self.__dict__.get("_num_params", len(self.param_ranges))
+
+    @num_params.setter
+    def num_params(self, value) -> None:
+        self.__dict__["_num_params"] = int(value)
 
     # subclasses with a packed kernel entry point set this to (callable(x, sr, packed), the process_fn it mirrors)
     _packed_path = None
@@ -67,10 +116,14 @@ class Processor:
                     f"Parameter tensor has {param_tensor.shape[1] if param_tensor.dim() == 2 else '?'} parameters, "
                     f"but processor has {len(self.param_ranges)} parameters."
                 )
-            if not self._range_check(param_tensor):
-                self.denormalize_param_dict(self.extract_param_dict(param_tensor))      # raises with the name
             scale, offset = self._affine(param_tensor.device)
-            return self._packed_path[0](x, self.sample_rate, torch.addcmul(offset, param_tensor.to(torch.float32), scale))
+            flag = self._flag(param_tensor.device)
+            phys = _DenormFn.apply(param_tensor, offset, scale, flag)
+            if self.strict_range_check and not torch.cuda.is_current_stream_capturing():
+                if int(flag.item()) != 0:
+                    flag.zero_()
+                    self.denormalize_param_dict(self.extract_param_dict(param_tensor))      # raises with the name
+            return self._packed_path[0](x, self.sample_rate, phys)
         param_dict = self.extract_param_dict(param_tensor)
         denorm = self.denormalize_param_dict(param_dict, _checked=self._range_check(param_tensor))
         return self.process_fn(x, self.sample_rate, **denorm)
@@ -84,6 +137,26 @@ class Processor:
             cache.clear()
             cache[key] = ((hi - lo).to(device), lo.to(device))
         return cache[key]
+
+    def _flag(self, device) -> torch.Tensor:
+        cache = self.__dict__.setdefault("_flag_cache", {})
+        key = str(device)
+        if key not in cache:
+            cache[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        return cache[key]
+
+    def range_violation(self, device=None) -> bool:
+        """True if a packed ``process_normalized`` call on ``device`` saw a parameter outside [0, 1] since the
+        last query (device->host read; meant for after a graph replay).  Resets the flag."""
+        flags = list(self.__dict__.get("_flag_cache", {}).items())
+        if device is not None:
+            flags = [(k, f) for k, f in flags if k == str(device)]
+        bad = False
+        for _, f in flags:
+            if int(f.item()) != 0:
+                bad = True
+                f.zero_()
+        return bad
 
     def process(self, x: torch.Tensor, *args):
         return self.process_fn(x, *args)
@@ -122,14 +195,21 @@ class Gain(Processor):
     def __init__(self, sample_rate: int, min_gain_db: float = -24.0, max_gain_db: float = 24.0):
         self.sample_rate = sample_rate
         self.process_fn = gain
+        self._packed_path = (lambda x, sr, p: gain(x, sr, p[:, 0]), gain)
         self.param_ranges = {"gain_db": (min_gain_db, max_gain_db)}
+        self.num_params = len(self.param_ranges)
 
 
 class Distortion(Processor):
-    def __init__(self, sample_rate: int = 44100, min_gain_db: float = 0.0, max_gain_db: float = 24.0):
+    """Reference order ``Distortion(min_gain_db, max_gain_db)`` (``modules.py:110-121``); ``sample_rate`` is a
+    trailing keyword (the reference class has none, which is why it cannot run ``process_normalized``)."""
+
+    def __init__(self, min_gain_db: float = 0.0, max_gain_db: float = 24.0, sample_rate: int = 44100):
         self.sample_rate = sample_rate
         self.process_fn = distortion
-        self.param_ranges = {"drive_db": (min_gain_db, max_gain_db)}
+        self._packed_path = (lambda x, sr, p: distortion(x, sr, p[:, 0]), distortion)
+        self.param_ranges = _RangeDict({"drive_db": (min_gain_db, max_gain_db)}, aliases={"gain_db": "drive_db"})
+        self.num_params = len(self.param_ranges)
 
 
 class ParametricEQ(Processor):

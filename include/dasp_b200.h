@@ -11,7 +11,10 @@
  *     arguments sized by the matching *_workspace_* query;
  *   - audio tensors are (batch, channels, samples) row-major, exactly the reference's
  *     tensor contract (README.md:38);
- *   - `stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises;
+ *   - `stream` is a cudaStream_t; all work is enqueued on it, nothing synchronises -- with ONE documented
+ *     exception: the first call on a device for a new (taps, sample_rate, geometry) builds library-owned caches
+ *     (cuFFT plans, filter-bank spectra, FFT twiddle tables: cudaMalloc + one cudaStreamSynchronize).  Warm the
+ *     shapes up once before capturing a CUDA graph; later calls are pure enqueues;
  *   - return value 0 = ok, negative = error (see DASP_ERR_*); the message is available
  *     from dasp_last_error() (thread-local).  No exception crosses this boundary;
  *   - reentrant from several host threads as long as they use distinct streams.
@@ -25,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DASP_ABI_VERSION 1
+#define DASP_ABI_VERSION 2
 
 #define DASP_OK 0
 #define DASP_ERR_INVALID (-1)   /* bad shape / null pointer / misalignment        */
@@ -40,6 +43,8 @@ const char* dasp_last_error(void);
 int dasp_compiled_arch(void);
 /* frees cached cuFFT plans and device-side filter-bank spectra */
 void dasp_shutdown(void);
+/* The dasp_debug_* entry points are TEST HOOKS: process-global switches, not thread-safe, not for production
+ * callers (they exist so that every kernel variant can be pinned against the oracle at small sizes). */
 /* test hook: pin the warps-per-row variant of the scan kernels (1, 2, 4, 8; 0 = automatic choice) */
 void dasp_debug_force_warps(int warps);
 /* test hook, IR synthesis of the device-noise reverb (all variants draw the same Philox stream and must agree):
@@ -49,6 +54,17 @@ void dasp_debug_reverb_path(int path);
 /* test hook: variant used by the last chunk of the most recent dasp_reverb_fwd: 0 = cuFFT pipeline, 1 = cluster
    kernel, 2 = generator + fused FFT/shaping kernel */
 int dasp_debug_reverb_last_path(void);
+
+/* test hook: 1 = the spectral IR synthesis uses unit-impulse filters, so the f_save buffer of dasp_reverb_fwd
+   returns the periodic white sequences w_k themselves (used to rebuild a reference-style noise tensor) */
+void dasp_debug_reverb_flat_filterbank(int on);
+
+/* ---- Processor.denormalize_param_dict on the device      (reference modules.py:13-14, 70-91) ------
+ * out[r][c] = lo[c] + p01[r][c] * span[c].  The reference's range check (ValueError when a value leaves [0, 1])
+ * cannot raise from the device: an offending element becomes NaN and bit 0 of *flag (device int, may be NULL)
+ * is set; the host reads the flag whenever it can afford to (modules.Processor does so outside graph capture). */
+int dasp_denormalize(const float* p01, const float* lo /* [cols] */, const float* span /* [cols] */, float* out,
+                     int* flag, int64_t rows, int64_t cols, void* stream);
 
 /* ---- gain: y = x * 10^(gain_db/20)            (reference functional.py:10-29) ------ */
 int dasp_gain_fwd(const float* x, const float* gain_db /* [bs] */, float* y, int64_t bs, int64_t chs,
@@ -121,7 +137,9 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
  *      signal.octave_band_filterbank signal.py:42-92) --------------------------------------
  * params is [bs][25] = 12 band gains, 12 band decays, mix (signature order).  x is (bs, in_chs, n)
  * with in_chs 1 or 2; y is always (bs, 2, n) (mono is duplicated, functional.py:493-495).
- * noise: NULL -> white noise is generated on the device (Philox4x32-10, keyed by `seed`);
+ * noise: NULL -> white noise is generated on the device (Philox4x32-10, keyed by the 64-bit value the kernels read
+ *        from the DEVICE pointer `seed_dev` when they run -- so a captured CUDA graph draws fresh noise on every
+ *        replay as long as the caller's graph also refreshes that word, as torch's graph-safe generator does);
  *        else the (bs*2, 12, num_samples + taps - 1) tensor the reference would have drawn
  *        (functional.py:547-548) -- the parity-test entry.
  * Buffers kept for the backward (pass NULL for all four when no backward follows):
@@ -142,7 +160,7 @@ typedef struct dasp_reverb_geom {
 } dasp_reverb_geom;
 int dasp_reverb_geometry(int64_t bs, int64_t n, int64_t num_samples, int64_t taps, int64_t chunk_items,
                          dasp_reverb_geom* out);
-int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const float* noise, uint64_t seed,
+int dasp_reverb_fwd(const float* x, int64_t in_chs, const float* params, const float* noise, const uint64_t* seed_dev,
                     float* y, float* wet_save, float* f_save, void* xspec_save, void* irspec_save,
                     void* workspace, int64_t workspace_bytes, int64_t bs, int64_t n, int64_t num_samples,
                     int64_t taps, int64_t chunk_items, float sample_rate, void* stream);

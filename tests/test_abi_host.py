@@ -26,7 +26,7 @@ def test_header_symbols_exported(lib):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/dasp_b200.h but not exported"
     assert declared == set(_abi.exported_symbols()), declared ^ set(_abi.exported_symbols())
-    assert lib.dasp_abi_version() == 1 and lib.dasp_compiled_arch() == 1000
+    assert lib.dasp_abi_version() == _abi.ABI_VERSION == 2 and lib.dasp_compiled_arch() == 1000
 
 
 def test_sm100a_sass_and_tma(lib):

@@ -39,7 +39,7 @@ def test_process_normalized_fast_path_matches_functional(cuda_device):
     pg = torch.rand(bs, 1, device=cuda_device)
     assert torch.allclose(D.Gain(SR).process_normalized(x, pg), D.gain(x, SR, pg[:, 0] * 48 - 24), rtol=1e-6, atol=0)
     xm = x[:, :1].contiguous()
-    assert torch.allclose(D.Distortion(SR).process_normalized(xm, pg), D.distortion(xm, SR, pg[:, 0] * 24), atol=1e-6)
+    assert torch.allclose(D.Distortion(sample_rate=SR).process_normalized(xm, pg), D.distortion(xm, SR, pg[:, 0] * 24), atol=1e-6)
 
 
 def test_process_normalized_errors_and_repointing(cuda_device):
@@ -112,3 +112,80 @@ def test_chain_cuda_graph_capture(cuda_device):
     graph.replay()
     torch.cuda.synchronize()
     assert not torch.allclose(x.grad, ref_gx)
+
+
+def test_processor_chain_graph_capture_with_device_noise(cuda_device):
+    """the chain the reference trains (examples/style_transfer.py:150-154: eq -> comp -> reverb ->
+    gain, all through Processor.process_normalized) captured fwd+bwd in ONE CUDA graph with the DEFAULT device-noise
+    reverb: no host read happens under capture (device-side range check), and -- like the reference's torch.randn --
+    every replay draws FRESH noise, because the Philox key is a device word re-drawn by torch's graph-safe generator.
+    A replay right after torch.manual_seed(s) equals the eager step after the same seed."""
+    import dasp_pytorch_b200 as D
+    bs, n, L, taps = 4, 8192, 6000, 255
+    torch.manual_seed(3)
+    x = (torch.rand(bs, 2, n, device=cuda_device) * 2 - 1).requires_grad_(True)
+    p = torch.rand(bs, 18 + 6 + 25 + 1, device=cuda_device)
+    p[:, 22].clamp_(min=0.05)                                          # knee > 0
+    p.requires_grad_(True)
+    eq, comp, gain = D.ParametricEQ(SR), D.Compressor(SR), D.Gain(SR)
+    rev = D.NoiseShapedReverb(SR)
+    import functools
+    from dasp_pytorch_b200 import functional as F
+    rev._packed_path = (functools.partial(F.noise_shaped_reverberation_packed, num_samples=L, num_bandpass_taps=taps),
+                        rev.process_fn)
+
+    def step():
+        y = eq.process_normalized(x, p[:, :18])
+        y = comp.process_normalized(y, p[:, 18:24])
+        y = rev.process_normalized(y, p[:, 24:49])
+        y = gain.process_normalized(y, p[:, 49:50])
+        loss = y.pow(2).mean()
+        loss.backward()
+        return y, loss
+
+    def eager(seed):
+        x.grad = None; p.grad = None
+        torch.manual_seed(seed)
+        y, loss = step()
+        return y.detach().clone(), loss.detach().clone(), x.grad.clone(), p.grad.clone()
+
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            eager(0)
+    torch.cuda.current_stream().wait_stream(side)
+    ref = eager(11)
+
+    x.grad = None; p.grad = None
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        ys, losss = step()
+    outs = []
+    for seed in (11, None):
+        with torch.no_grad():
+            x.grad.zero_(); p.grad.zero_()
+        if seed is not None:
+            torch.manual_seed(seed)
+        graph.replay()
+        torch.cuda.synchronize()
+        outs.append((ys.clone(), losss.clone(), x.grad.clone(), p.grad.clone()))
+    # replay after manual_seed(11) == eager after manual_seed(11)
+    for a, b in zip(outs[0], ref):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), float((a - b).abs().max())
+    # the next replay drew different noise: wet part differs, nothing is NaN
+    assert torch.isfinite(outs[1][0]).all()
+    assert float((outs[1][0] - outs[0][0]).abs().max()) > 1e-3 * float(outs[0][0].abs().max())
+    assert not (eq.range_violation() or comp.range_violation() or rev.range_violation())
+    # device-side range check under capture: an out-of-range value poisons its item and raises the flag, no exception
+    with torch.no_grad():
+        p[1, 20] = 1.5
+    graph.replay()
+    torch.cuda.synchronize()
+    assert comp.range_violation() and not comp.range_violation()        # reported once, then reset
+    assert torch.isnan(ys[1]).any() and torch.isfinite(ys[0]).all()
+    with torch.no_grad():
+        p[1, 20] = 0.5
+    with pytest.raises(ValueError, match="attack_ms"):                  # eager: the reference's ValueError
+        bad = p.detach().clone(); bad[0, 20] = -0.2
+        comp.process_normalized(x.detach(), bad[:, 18:24])

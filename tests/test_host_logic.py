@@ -43,7 +43,27 @@ def test_processor_ranges_and_order():
     rv = D.NoiseShapedReverb(44100)
     assert rv.num_params == 25 and list(rv.param_ranges)[12] == "band0_decay" and list(rv.param_ranges)[24] == "mix"
     assert D.Gain(44100).param_ranges == {"gain_db": (-24.0, 24.0)}
-    assert D.Distortion(44100).param_ranges == {"drive_db": (0.0, 24.0)}
+    assert D.Distortion().param_ranges == {"drive_db": (0.0, 24.0)}
+
+
+def test_reference_constructor_compat():
+    """drop-in details of the reference classes (modules.py:94-121 upstream): ``Distortion(min, max)`` positional
+    order, the reference's ``gain_db`` key still resolves, ``num_params`` is assignable like in every reference
+    subclass (user-defined processors do ``self.num_params = len(self.param_ranges)``)."""
+    d = D.Distortion(0.0, 12.0)
+    assert d.param_ranges["drive_db"] == (0.0, 12.0) and d.param_ranges["gain_db"] == (0.0, 12.0)
+    assert list(d.param_ranges) == ["drive_db"] and d.num_params == 1 and d.sample_rate == 44100
+    assert D.Distortion(sample_rate=48000).sample_rate == 48000
+
+    class Mine(D.Processor):
+        def __init__(self):
+            self.process_fn = lambda x, sr, **kw: x
+            self.param_ranges = {"a": (0.0, 1.0), "b": (1.0, 2.0)}
+            self.num_params = len(self.param_ranges)          # AttributeError in round 1
+
+    m = Mine()
+    assert m.num_params == 2
+    assert m.process_normalized(torch.zeros(1, 1, 4), torch.rand(1, 2)).shape == (1, 1, 4)
 
 
 def test_process_normalized_contract():
