@@ -41,6 +41,7 @@ _SIGNATURES = {
     "dasp_compiled_arch": (c_int, []),
     "dasp_shutdown": (None, []),
     "dasp_debug_force_warps": (None, [c_int]),
+    "dasp_debug_eq_bwd_stages": (None, [c_int]),
     "dasp_debug_reverb_path": (None, [c_int]),
     "dasp_debug_reverb_last_path": (c_int, []),
     "dasp_debug_reverb_flat_filterbank": (None, [c_int]),
@@ -58,6 +59,7 @@ _SIGNATURES = {
     "dasp_bus_fwd": (c_int, [P, P, P, I64, I64, I64, P]),
     "dasp_bus_bwd": (c_int, [P, P, P, P, P, P, I64, I64, I64, I64, P]),
     "dasp_eq_tile_len": (I64, [I64]),
+    "dasp_eq_ckpt_floats": (I64, [I64, I64, I64]),
     "dasp_eq_bwd_workspace_floats": (I64, [I64, I64]),
     "dasp_eq_fwd": (c_int, [P, P, P, P, I64, I64, I64, c_float, P]),
     "dasp_eq_bwd": (c_int, [P, P, P, P, P, P, P, I64, I64, I64, I64, c_float, P]),

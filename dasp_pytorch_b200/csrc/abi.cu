@@ -35,6 +35,8 @@ int debug_forced_warps() { return g_forced_warps; }
 static int g_reverb_path = 0;
 int debug_reverb_path() { return g_reverb_path; }
 
+static int g_eq_bwd_stages = 0;
+int debug_eq_bwd_stages() { return g_eq_bwd_stages; }
 static int g_flat_fb = 0;
 int debug_flat_filterbank() { return g_flat_fb; }
 
@@ -77,6 +79,8 @@ int dasp_denormalize(const float* p01, const float* lo, const float* span, float
   DASP_LAUNCH_OK("denormalize_kernel");
   return DASP_OK;
 }
+
+void dasp_debug_eq_bwd_stages(int stages) { dasp::g_eq_bwd_stages = (stages == 1 || stages == 2) ? stages : 0; }
 
 void dasp_debug_reverb_flat_filterbank(int on) { dasp::g_flat_fb = on ? 1 : 0; }
 

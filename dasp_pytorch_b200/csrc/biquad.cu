@@ -18,26 +18,38 @@
 // measured against the fp64 reference this is 100-1000x more accurate than the reference's own
 // fp32 path (numerics table).  Coefficients and all matrix powers are designed in fp64.
 //
-// Parallelisation.  One CTA per (item, channel) row walks its N samples through the TMA tile
-// pipeline (tile_pipe.cuh).  In a tile each thread owns E consecutive samples and, per section:
-//   local zero-state pass -> Kogge-Stone shuffle scan of the 2-vector end states with the
-//   precomputed powers A^(E*2^k) -> cross-warp carry in shared memory -> fix-up
-//   y[j] += (A^j c_in)_1 from a per-item table.  (A is constant in time, so the scan operator is
-//   a matrix power, not a generic 2x2 pair product.)
-// The tile-to-tile carries stay in registers; the forward stores them per tile as checkpoints.
+// Parallelisation (round 2: "row pairs on FFMA2, warps decoupled along time").
+//   * Two rows (the left/right channel of an item when C = 2; any two consecutive rows otherwise) are the two
+//     lanes of Blackwell's packed fp32x2 instructions (FFMA2 / FMUL2 / FADD2): one issue slot, two FMAs.  The
+//     kernels are instruction-issue bound (about 100 fp32 instructions per sample in the scalar round-1 form,
+//     at the fp32 ridge of the chip), so this halves the cost per sample.  All tables hold (row A, row B) pairs.
+//   * One CTA per row pair, W warps.  The row is cut into tiles of 32*E samples; warp w owns tiles w, w+W, ...
+//     and runs the WHOLE cascade on a tile with the data in registers: per section a zero-state local pass over
+//     the lane's E samples, a Kogge-Stone shuffle scan of the lanes' end states with the precomputed powers
+//     A^(E 2^k) (A is constant in time, so the scan operator is a matrix power, not a generic 2x2 product), and a
+//     fix-up  y[j] += (A^j c_in)_1  from a per-pair table.
+//   * The only coupling between consecutive tiles of a row is the 2-vector carry of each section,
+//     c(i+1) = A^(32E) c(i) + total(i).  It travels from the warp of tile i to the warp of tile i+1 through a
+//     16-byte shared-memory mailbox guarded by an mbarrier (arrive = release, try_wait = acquire): no block
+//     barrier anywhere in the main loop, the W warps drift freely and hide each other's scan/shuffle latency.
+//     (The round-1 kernels synchronised the whole CTA once per section per tile and were latency bound.)
+//   * Every warp streams its own tiles HBM -> shared memory -> HBM with 1-D TMA bulk copies (UBLKCP) and its own
+//     mbarriers/bulk groups, double buffered; the hot loop contains no LDG/STG for audio.
+// The forward stores the section states entering every tile (24 floats per tile per pair) as checkpoints.
 //
 // Backward.  State-space adjoint (SURVEY.md A.3 restated for the sigma form): with lam = adjoint
 // state,  lam[n] = A^T lam[n+1] + (g[n],0);  gu[n] = be1*lam1[n+1] + B2*lam2[n+1] + b0*g[n];
 //   d sg = sum lam[n+1].s[n],  d q = sum lam2[n+1] s1[n],  d be1 = sum lam1[n+1] u[n],
 //   d B2 = sum lam2[n+1] u[n], d b0 = sum g[n] u[n].
-// Tiles are swept in reverse time order; per tile the six section inputs are recomputed from the
-// checkpoint into thread-private shared memory, then sections are unwound 6 -> 1.  The 30 sums per
-// row are reduced deterministically; a second tiny kernel adds the channels of an item and applies
+// Tiles are swept in reverse time order with the same warp/mailbox structure (the adjoint carry flows from tile
+// i+1 to tile i); per tile the six section inputs are recomputed from the checkpoint into per-warp shared memory
+// (no cross-tile dependency: every tile's incoming states are checkpointed), then sections are unwound 6 -> 1.
+// The 30 sums per row are reduced deterministically; a second tiny kernel adds the channels of an item and applies
 // the fp64 Jacobian d(sg,q,be1,B2,b0)/d(gain_dB, fc, Q) (forward-mode dual numbers).
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
-#include "tile_pipe.cuh"
 
 namespace dasp {
 namespace {
@@ -45,13 +57,11 @@ namespace {
 #ifndef DASP_EQ_E
 #define DASP_EQ_E 15
 #endif
-#ifndef DASP_EQ_WARPS_PER_SM
-#define DASP_EQ_WARPS_PER_SM 24
-#endif
-constexpr int kE = DASP_EQ_E;    // samples per thread per tile (odd: conflict-free stride-E smem access)
-constexpr int kStages = 3;
+constexpr int kE = DASP_EQ_E;    // samples per lane per tile (odd: conflict-free stride-E shared-memory access)
+static_assert(kE % 2 == 1, "E must be odd");
+constexpr int kTile = 32 * kE;   // samples per tile (one warp)
 constexpr int kSections = 6;
-constexpr int kNumPowTables = kE + 5 + 32 + 1;   // A^j (j<E) | A^(E 2^k) (k<5) | A^(E lane) | A^(32E)
+constexpr int kFwdStages = 2;
 
 // ------------------------------------------------------------------ coefficient design (fp64)
 // forward-mode dual number with 3 directional derivatives (gain_dB, fc, Q)
@@ -134,299 +144,476 @@ __device__ inline M2d mpow(double sg, double q, unsigned n) {
   return r;
 }
 
-// ------------------------------------------------------------------ shared-memory layout
-// per-item tables (fp32), built once per CTA
-struct __align__(16) EqTables {
-  float cf[kSections][8];              // sg, q, be1, B2, b0, pad
-  float4 pw[kSections][kNumPowTables]; // (a,b,c,d) of the powers listed at kNumPowTables
-};
-__device__ __forceinline__ const float4& pw_j(const EqTables& t, int k, int j) { return t.pw[k][j]; }            // A^j
-__device__ __forceinline__ const float4& pw_step(const EqTables& t, int k, int s) { return t.pw[k][kE + s]; }    // A^(E 2^s)
-__device__ __forceinline__ const float4& pw_lane(const EqTables& t, int k, int l) { return t.pw[k][kE + 5 + l]; }  // A^(E l)
-__device__ __forceinline__ const float4& pw_warp(const EqTables& t, int k) { return t.pw[k][kE + 5 + 32]; }       // A^(32E)
+// ------------------------------------------------------------------ packed fp32x2 helpers (x = row A, y = row B)
+typedef float2 f2;
+__device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ f2 fmul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f2 fadd2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f2 zero2() { return make_float2(0.f, 0.f); }
+__device__ __forceinline__ f2 shfl_up2(f2 v, int d) {
+  return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ f2 shfl_down2(f2 v, int d) {
+  return make_float2(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d));
+}
+__device__ __forceinline__ f2 shfl2(f2 v, int l) {
+  return make_float2(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l));
+}
+struct St { f2 s1, s2; };                     // the 2-state vector of both rows
+struct M4 { f2 a, b, c, d; };                 // 2x2 matrix per row: [[a,b],[c,d]]
+__device__ __forceinline__ M4 ldm(const f2* p) {
+  const float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 2);
+  return {make_float2(lo.x, lo.y), make_float2(lo.z, lo.w), make_float2(hi.x, hi.y), make_float2(hi.z, hi.w)};
+}
+__device__ __forceinline__ St mv(const M4& m, const St& v) {          // M v
+  return {ffma2(m.a, v.s1, fmul2(m.b, v.s2)), ffma2(m.c, v.s1, fmul2(m.d, v.s2))};
+}
+__device__ __forceinline__ St mtv(const M4& m, const St& v) {         // M^T v
+  return {ffma2(m.a, v.s1, fmul2(m.c, v.s2)), ffma2(m.b, v.s1, fmul2(m.d, v.s2))};
+}
+__device__ __forceinline__ St mv_acc(const M4& m, const St& v, const St& acc) {     // acc + M v
+  return {ffma2(m.a, v.s1, ffma2(m.b, v.s2, acc.s1)), ffma2(m.c, v.s1, ffma2(m.d, v.s2, acc.s2))};
+}
+__device__ __forceinline__ St mtv_acc(const M4& m, const St& v, const St& acc) {    // acc + M^T v
+  return {ffma2(m.a, v.s1, ffma2(m.c, v.s2, acc.s1)), ffma2(m.b, v.s1, ffma2(m.d, v.s2, acc.s2))};
+}
 
-constexpr size_t kHdrBars = 64;                                   // S mbarriers
-constexpr size_t kHdrAgg = 16 * 2 * 8 * sizeof(float2);           // up to 16 scan slots x 8 warps (double-buffered by slot)
-constexpr size_t kHdr = ((kHdrBars + kHdrAgg + sizeof(EqTables) + 127) / 128) * 128;
-
-struct Smem {
-  uint64_t* bars; float2* agg; EqTables* tb; float* stages;
-  __device__ __forceinline__ Smem(unsigned char* base) {
-    bars = reinterpret_cast<uint64_t*>(base);
-    agg = reinterpret_cast<float2*>(base + kHdrBars);
-    tb = reinterpret_cast<EqTables*>(base + kHdrBars + kHdrAgg);
-    stages = reinterpret_cast<float*>(base + kHdr);
-  }
+// ------------------------------------------------------------------ shared-memory tables of one row pair
+constexpr int kStepSlots = 6;     // A^(E 2^s), s = 0..4, and the zero matrix (lanes a scan step does not touch)
+struct __align__(16) PairTables {
+  f2 cf[kSections][6];                    // sg, q, be1, B2, b0, pad
+  float4 fix[kSections][kE];              // first row of A^j: (a_j rowA, a_j rowB, b_j rowA, b_j rowB)
+  f2 step[kSections][kStepSlots][4];      // (a, b, c, d) pairs
+  f2 lane[kSections][32][4];              // A^(E l)
+  f2 warp[kSections][4];                  // A^(32 E)
 };
+constexpr int kPowPerSection = kE + 5 + 32 + 1;
 
 struct EqParams {
-  const float* x;        // (bs, C, N)
+  const float* x;        // (rows, N)
   const float* gy;       // backward
   float* y;              // forward out / backward gx
   const float* params;   // (bs, 18): gain_dB, fc, Q per section, signature order
-  float* ckpt;           // (rows, ntiles, 12): section states entering each tile
+  float* ckpt;           // (pairs, ntiles, 6) float4: section states (s1A, s1B, s2A, s2B) entering each tile
   float* partial;        // (rows, 30) backward: per-row coefficient-gradient sums
   int64_t n;
+  int64_t rows;
   int chs;
   int ntiles;
   float sample_rate;
   int bulk;
 };
 
-struct RowIO {    // forward: one buffer, in place
-  const float* src0; float* dst0;
-  __device__ __forceinline__ const float* src(int) const { return src0; }
-  __device__ __forceinline__ float* dst(int) const { return dst0; }
-};
-struct RowIOBwd { // backward: buffer 0 = x (read only), buffer 1 = gy -> gx
-  const float* x0; const float* g0; float* gx0;
-  __device__ __forceinline__ const float* src(int b) const { return b == 0 ? x0 : g0; }
-  __device__ __forceinline__ float* dst(int b) const { return b == 0 ? nullptr : gx0; }
-};
-
-// build the per-item tables: every thread of the CTA participates; ends with __syncthreads()
-__device__ void build_tables(EqTables& tb, const float* params18, float sample_rate) {
-  __shared__ double cfd[kSections][2];   // sg, q in fp64 for the matrix powers
-  const int tid = threadIdx.x;
-  if (tid < kSections) {
-    const SigmaCoef sc = design_section((double)params18[3 * tid], (double)params18[3 * tid + 1],
-                                        (double)params18[3 * tid + 2], (double)sample_rate, section_kind(tid));
+// build the tables of the pair (row A of item ia, row B of item ib): every thread of the CTA participates;
+// ends with __syncthreads()
+__device__ void build_tables(PairTables& tb, const float* params, int64_t ia, int64_t ib, float sample_rate) {
+  __shared__ double cfd[2][kSections][2];   // sg, q in fp64 for the matrix powers
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int halves = (ia == ib) ? 1 : 2;
+  for (int e = tid; e < halves * kSections; e += nthr) {
+    const int h = e / kSections, k = e - h * kSections;
+    const float* p18 = params + (h == 0 ? ia : ib) * 18;
+    const SigmaCoef sc = design_section((double)p18[3 * k], (double)p18[3 * k + 1], (double)p18[3 * k + 2],
+                                        (double)sample_rate, section_kind(k));
+    float* cf = reinterpret_cast<float*>(&tb.cf[k][0]);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) tb.cf[tid][j] = (float)sc.c[j].v;
-    tb.cf[tid][5] = tb.cf[tid][6] = tb.cf[tid][7] = 0.f;
-    cfd[tid][0] = sc.c[0].v;
-    cfd[tid][1] = sc.c[1].v;
+    for (int j = 0; j < 5; ++j) {
+      const float v = (float)sc.c[j].v;
+      if (halves == 1) { cf[2 * j] = v; cf[2 * j + 1] = v; } else { cf[2 * j + h] = v; }
+    }
+    if (halves == 1 || h == 0) { cf[10] = 0.f; cf[11] = 0.f; }
+    cfd[h][k][0] = sc.c[0].v;
+    cfd[h][k][1] = sc.c[1].v;
   }
   __syncthreads();
-  for (int idx = tid; idx < kSections * kNumPowTables; idx += blockDim.x) {
-    const int k = idx / kNumPowTables, e = idx - k * kNumPowTables;
+  for (int idx = tid; idx < halves * kSections * kPowPerSection; idx += nthr) {
+    const int h = idx / (kSections * kPowPerSection);
+    const int r = idx - h * (kSections * kPowPerSection);
+    const int k = r / kPowPerSection, e = r - k * kPowPerSection;
     unsigned n;
     if (e < kE) n = (unsigned)e;
     else if (e < kE + 5) n = (unsigned)kE << (e - kE);
     else if (e < kE + 5 + 32) n = (unsigned)(kE * (e - kE - 5));
     else n = (unsigned)(kE * 32);
-    const M2d m = mpow(cfd[k][0], cfd[k][1], n);
-    tb.pw[k][e] = make_float4((float)m.a, (float)m.b, (float)m.c, (float)m.d);
+    const M2d m = mpow(cfd[h][k][0], cfd[h][k][1], n);
+    const float ma = (float)m.a, mb = (float)m.b, mc = (float)m.c, md = (float)m.d;
+    if (e < kE) {
+      float* f = reinterpret_cast<float*>(&tb.fix[k][e]);
+      if (halves == 1) { f[0] = ma; f[1] = ma; f[2] = mb; f[3] = mb; } else { f[h] = ma; f[2 + h] = mb; }
+    } else {
+      float* f;
+      if (e < kE + 5) f = reinterpret_cast<float*>(&tb.step[k][e - kE][0]);
+      else if (e < kE + 5 + 32) f = reinterpret_cast<float*>(&tb.lane[k][e - kE - 5][0]);
+      else f = reinterpret_cast<float*>(&tb.warp[k][0]);
+      if (halves == 1) { f[0] = ma; f[1] = ma; f[2] = mb; f[3] = mb; f[4] = mc; f[5] = mc; f[6] = md; f[7] = md; }
+      else { f[h] = ma; f[2 + h] = mb; f[4 + h] = mc; f[6 + h] = md; }
+    }
   }
+  for (int e = tid; e < kSections * 8; e += nthr) reinterpret_cast<float*>(&tb.step[e / 8][5][0])[e % 8] = 0.f;
   __syncthreads();
 }
 
-// ------------------------------------------------------------------ 2-state block scans
-__device__ __forceinline__ float2 mv(const float4& m, float2 v) {          // M v
-  return make_float2(fmaf(m.x, v.x, m.y * v.y), fmaf(m.z, v.x, m.w * v.y));
-}
-__device__ __forceinline__ float2 mtv(const float4& m, float2 v) {         // M^T v
-  return make_float2(fmaf(m.x, v.x, m.z * v.y), fmaf(m.y, v.x, m.w * v.y));
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-
-// forward in time: v = this thread's end state after a zero-state local pass; c_tile = state entering
-// the tile (updated to the state leaving it).  Returns the state entering this thread's chunk.
-template <int W>
-__device__ __forceinline__ float2 scan_fwd2(float2 v, float2& c_tile, const EqTables& tb, int k, float2* agg,
-                                            int lane, int warp) {
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    float2 u;
-    u.x = __shfl_up_sync(0xffffffffu, v.x, 1 << s);
-    u.y = __shfl_up_sync(0xffffffffu, v.y, 1 << s);
-    if (lane >= (1 << s)) v = add2(v, mv(pw_step(tb, k, s), u));
-  }
-  float2 excl;
-  excl.x = __shfl_up_sync(0xffffffffu, v.x, 1);
-  excl.y = __shfl_up_sync(0xffffffffu, v.y, 1);
-  if (lane == 0) excl = make_float2(0.f, 0.f);
-  float2 c_warp = c_tile;
-  const float4 wm = pw_warp(tb, k);
-  if (W > 1) {
-    if (lane == 31) agg[warp] = v;
-    __syncthreads();
-    float2 c = c_tile;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-      if (w == warp) c_warp = c;
-      c = add2(mv(wm, c), agg[w]);
-    }
-    c_tile = c;
-  } else {
-    float2 tot;
-    tot.x = __shfl_sync(0xffffffffu, v.x, 31);
-    tot.y = __shfl_sync(0xffffffffu, v.y, 31);
-    c_tile = add2(mv(wm, c_tile), tot);
-  }
-  return add2(excl, mv(pw_lane(tb, k, lane), c_warp));
-}
-
-// reverse in time (adjoint): v = adjoint state at this thread's first sample after a zero-terminal local
-// reverse pass; c_tile = adjoint state at the first sample of the NEXT tile.  Uses transposed powers.
-template <int W>
-__device__ __forceinline__ float2 scan_rev2(float2 v, float2& c_tile, const EqTables& tb, int k, float2* agg,
-                                            int lane, int warp) {
-#pragma unroll
-  for (int s = 0; s < 5; ++s) {
-    float2 u;
-    u.x = __shfl_down_sync(0xffffffffu, v.x, 1 << s);
-    u.y = __shfl_down_sync(0xffffffffu, v.y, 1 << s);
-    if (lane + (1 << s) < 32) v = add2(v, mtv(pw_step(tb, k, s), u));
-  }
-  float2 excl;
-  excl.x = __shfl_down_sync(0xffffffffu, v.x, 1);
-  excl.y = __shfl_down_sync(0xffffffffu, v.y, 1);
-  if (lane == 31) excl = make_float2(0.f, 0.f);
-  float2 c_warp = c_tile;
-  const float4 wm = pw_warp(tb, k);
-  if (W > 1) {
-    if (lane == 0) agg[warp] = v;
-    __syncthreads();
-    float2 c = c_tile;
-#pragma unroll
-    for (int w = W - 1; w >= 0; --w) {
-      if (w == warp) c_warp = c;
-      c = add2(mtv(wm, c), agg[w]);
-    }
-    c_tile = c;
-  } else {
-    float2 tot;
-    tot.x = __shfl_sync(0xffffffffu, v.x, 0);
-    tot.y = __shfl_sync(0xffffffffu, v.y, 0);
-    c_tile = add2(mtv(wm, c_tile), tot);
-  }
-  // distance from the first sample of thread lane+1 to the first sample of the next warp: (31-lane) chunks
-  return add2(excl, mtv(pw_lane(tb, k, 31 - lane), c_warp));
-}
-
-struct Cf { float sg, q, be1, B2, b0; };
-__device__ __forceinline__ Cf load_cf(const EqTables& tb, int k) {
+struct Cf { f2 sg, q, be1, B2, b0; };
+__device__ __forceinline__ Cf load_cf(const PairTables& tb, int k) {
   const float4 a = *reinterpret_cast<const float4*>(&tb.cf[k][0]);
-  return {a.x, a.y, a.z, a.w, tb.cf[k][4]};
+  const float4 b = *reinterpret_cast<const float4*>(&tb.cf[k][2]);
+  return {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w), tb.cf[k][4]};
 }
 
-// zero-state local pass of section k over the thread's E samples (in place); returns the end state
-__device__ __forceinline__ float2 local_pass(float (&v)[kE], const Cf& c) {
-  float s1 = 0.f, s2 = 0.f;
+// zero-state local pass of section k over the lane's E samples (in place); returns the end state.
+// Two dependent packed operations per sample on the (s1, s2) recurrence.
+__device__ __forceinline__ St local_pass(f2 (&v)[kE], const Cf& c) {
+  f2 s1 = zero2(), s2 = zero2();
 #pragma unroll
   for (int j = 0; j < kE; ++j) {
-    const float u = v[j];
-    v[j] = fmaf(c.b0, u, s1);
-    const float t1 = fmaf(c.be1, u, fmaf(c.sg, s1, s2));
-    s2 = fmaf(c.B2, u, fmaf(c.q, s1, c.sg * s2));
-    s1 = t1;
+    const f2 u = v[j];
+    v[j] = ffma2(c.b0, u, s1);
+    const f2 a = ffma2(c.be1, u, s2);
+    const f2 b = ffma2(c.q, s1, fmul2(c.B2, u));
+    s1 = ffma2(c.sg, s1, a);
+    s2 = ffma2(c.sg, s2, b);
   }
-  return make_float2(s1, s2);
+  return {s1, s2};
 }
+
+// ------------------------------------------------------------------ warp scans of the lanes' 2-vectors
+// per-lane byte offsets of the step matrices: the real power where the Kogge-Stone step applies to this lane, the
+// zero matrix otherwise (so the step is 2 LDS.128 + 4 SHFL + 4 FFMA2 without predicates or selects)
+struct StepOffsets { int o[5]; };
+__device__ __forceinline__ StepOffsets fwd_offsets(int lane) {
+  StepOffsets s;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) s.o[i] = (lane >= (1 << i)) ? i : 5;
+  return s;
+}
+__device__ __forceinline__ StepOffsets rev_offsets(int lane) {
+  StepOffsets s;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) s.o[i] = (lane + (1 << i) < 32) ? i : 5;
+  return s;
+}
+
+// forward in time.  v: end state of the lane's zero-state local pass.  Returns the inclusive scan; `excl` = the
+// contribution of the lower lanes to the state entering this lane's chunk, `tot` = lane 31's inclusive value.
+__device__ __forceinline__ void scan_fwd(St v, const PairTables& tb, int k, const StepOffsets& so, int lane, St& excl,
+                                         St& tot) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const St u = {shfl_up2(v.s1, 1 << s), shfl_up2(v.s2, 1 << s)};
+    v = mv_acc(ldm(&tb.step[k][so.o[s]][0]), u, v);
+  }
+  excl = {shfl_up2(v.s1, 1), shfl_up2(v.s2, 1)};
+  if (lane == 0) excl = {zero2(), zero2()};
+  tot = {shfl2(v.s1, 31), shfl2(v.s2, 31)};
+}
+// reverse in time (adjoint): v = adjoint state at the lane's first sample after a zero-terminal local reverse pass
+__device__ __forceinline__ void scan_rev(St v, const PairTables& tb, int k, const StepOffsets& so, int lane, St& excl,
+                                         St& tot) {
+#pragma unroll
+  for (int s = 0; s < 5; ++s) {
+    const St u = {shfl_down2(v.s1, 1 << s), shfl_down2(v.s2, 1 << s)};
+    v = mtv_acc(ldm(&tb.step[k][so.o[s]][0]), u, v);
+  }
+  excl = {shfl_down2(v.s1, 1), shfl_down2(v.s2, 1)};
+  if (lane == 31) excl = {zero2(), zero2()};
+  tot = {shfl2(v.s1, 0), shfl2(v.s2, 0)};
+}
+
+// ------------------------------------------------------------------ carry mailboxes between the warps of a CTA
+// mailbox (k, w): carry of section k entering the next tile of warp w; written by the warp of the preceding tile.
+// Use number u of a mailbox completes phase u of its mbarrier (tile/sequence 0 is pre-arrived with a zero carry).
+template <int W>
+struct Mail {
+  float4* data;     // [kSections][W]
+  uint64_t* bar;    // [kSections][W]
+  __device__ __forceinline__ void init_all() {       // thread 0, before the CTA-wide barrier
+    for (int i = 0; i < kSections * W; ++i) mbar_init(&bar[i], 1);
+    fence_barrier_init();
+    for (int k = 0; k < kSections; ++k) {
+      data[k * W + 0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      mbar_arrive(&bar[k * W + 0]);
+    }
+  }
+  __device__ __forceinline__ St take(int k, int w, int use) {
+    mbar_wait(&bar[k * W + w], (uint32_t)(use & 1));
+    const float4 d = data[k * W + w];
+    __syncwarp();                                    // every lane has its copy before lane 0 may trigger a refill
+    return {make_float2(d.x, d.y), make_float2(d.z, d.w)};
+  }
+  __device__ __forceinline__ void put(int k, int w, const St& c, int lane) {
+    if (lane == 0) {
+      data[k * W + w] = make_float4(c.s1.x, c.s1.y, c.s2.x, c.s2.y);
+      mbar_arrive(&bar[k * W + w]);
+    }
+  }
+};
+
+// ------------------------------------------------------------------ per-warp tile I/O (TMA bulk copies)
+// A "unit" is the pair's two row tiles: [row A: kTile floats][row B: kTile floats].
+constexpr int kUnitFloats = 2 * kTile;
+
+struct RowPair {
+  int64_t n; int ntiles; bool bulk; bool has_b;
+  __device__ __forceinline__ int len_of(int tile) const {
+    const int64_t rem = n - (int64_t)tile * kTile;
+    return rem < kTile ? (int)rem : kTile;
+  }
+};
+
+// load tile `tile` of rows (a, b) into `unit`; bulk: lane 0 issues, completion on `bar`; else cooperative + __syncwarp
+__device__ __forceinline__ void warp_load(float* unit, const float* a, const float* b, int tile, const RowPair& rp,
+                                          uint64_t* bar, int lane) {
+  const int64_t pos = (int64_t)tile * kTile;
+  const int len = rp.len_of(tile);
+  if (rp.bulk) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar, (uint32_t)len * 8u);
+      tma_load_1d(unit, a + pos, (uint32_t)len * 4u, bar);
+      tma_load_1d(unit + kTile, b + pos, (uint32_t)len * 4u, bar);
+    }
+  } else {
+    for (int i = lane; i < len; i += 32) { unit[i] = a[pos + i]; unit[kTile + i] = b[pos + i]; }
+    __syncwarp();
+  }
+}
+__device__ __forceinline__ void warp_store(const float* unit, float* a, float* b, int tile, const RowPair& rp, int lane) {
+  const int64_t pos = (int64_t)tile * kTile;
+  const int len = rp.len_of(tile);
+  if (rp.bulk) {
+    fence_proxy_async_smem();         // my generic-proxy writes -> visible to the TMA engine
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_1d(a + pos, unit, (uint32_t)len * 4u);
+      if (rp.has_b) tma_store_1d(b + pos, unit + kTile, (uint32_t)len * 4u);
+      tma_store_commit();
+    }
+  } else {
+    __syncwarp();
+    for (int i = lane; i < len; i += 32) { a[pos + i] = unit[i]; if (rp.has_b) b[pos + i] = unit[kTile + i]; }
+    __syncwarp();
+  }
+}
+
+// dynamic shared memory carve-up
+template <int W, int UNITS_PER_WARP, int BARS_PER_WARP>
+struct Smem {
+  PairTables* tb; float4* mail_data; uint64_t* mail_bar; uint64_t* full; float* units;
+  static constexpr size_t kTab = (sizeof(PairTables) + 127) / 128 * 128;
+  static constexpr size_t kMailData = sizeof(float4) * kSections * W;
+  static constexpr size_t kBars = sizeof(uint64_t) * (kSections * W + BARS_PER_WARP * W);
+  static constexpr size_t kHdr = (kTab + kMailData + kBars + 127) / 128 * 128;
+  static constexpr size_t kBytes = kHdr + sizeof(float) * kUnitFloats * UNITS_PER_WARP * W;
+  __device__ __forceinline__ explicit Smem(unsigned char* base) {
+    tb = reinterpret_cast<PairTables*>(base);
+    mail_data = reinterpret_cast<float4*>(base + kTab);
+    mail_bar = reinterpret_cast<uint64_t*>(base + kTab + kMailData);
+    full = mail_bar + kSections * W;
+    units = reinterpret_cast<float*>(base + kHdr);
+  }
+};
 
 // =============================================================================== forward
 template <int W>
 __global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem sm(smem_raw);
-  EqTables& tb = *sm.tb;
-  const int row = blockIdx.x, item = row / p.chs;
+  using SM = Smem<W, kFwdStages, kFwdStages>;
+  SM sm(smem_raw);
+  const PairTables& tb = *sm.tb;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile_len = W * 32 * kE;
+  const int64_t row_a = 2 * (int64_t)blockIdx.x;
+  const bool has_b = row_a + 1 < p.rows;
+  const int64_t row_b = has_b ? row_a + 1 : row_a;
 
-  build_tables(tb, p.params + (int64_t)item * 18, p.sample_rate);
+  build_tables(*sm.tb, p.params, row_a / p.chs, row_b / p.chs, p.sample_rate);
+  Mail<W> mail{sm.mail_data, sm.mail_bar};
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kFwdStages * W; ++i) mbar_init(&sm.full[i], 1);
+    if (W > 1) mail.init_all(); else fence_barrier_init();
+  }
+  __syncthreads();
 
-  TileGeom g{p.n, tile_len, p.ntiles, false};
-  RowIO rows{p.x + (int64_t)row * p.n, p.y + (int64_t)row * p.n};
-  TilePipe<kStages> pipe;
-  pipe.init(sm.bars, sm.stages, 1, tile_len, p.bulk != 0);
-  pipe.prologue(g, rows);
+  const RowPair rp{p.n, p.ntiles, p.bulk != 0, has_b};
+  const float* xa = p.x + row_a * p.n;
+  const float* xb = p.x + row_b * p.n;
+  float* ya = p.y + row_a * p.n;
+  float* yb = p.y + row_b * p.n;
+  float* my_units = sm.units + (size_t)warp * kFwdStages * kUnitFloats;
+  uint64_t* my_full = sm.full + warp * kFwdStages;
+  const StepOffsets so = fwd_offsets(lane);
+  float4* ckpt = p.ckpt ? reinterpret_cast<float4*>(p.ckpt) + (int64_t)blockIdx.x * p.ntiles * kSections : nullptr;
 
-  float2 carry[kSections];
+  St carry[kSections];                      // W == 1: the tile-to-tile carries live in registers
 #pragma unroll
-  for (int k = 0; k < kSections; ++k) carry[k] = make_float2(0.f, 0.f);
-  const int off = threadIdx.x * kE;
+  for (int k = 0; k < kSections; ++k) carry[k] = {zero2(), zero2()};
 
-  for (int i = 0; i < p.ntiles; ++i) {
-    pipe.acquire(i, g, rows);
-    float* buf = pipe.buf(i % kStages, 0) + off;
-    const int64_t n0 = (int64_t)i * tile_len + off;
-    if (p.ckpt && threadIdx.x == 0) {
-      float2* ck = reinterpret_cast<float2*>(p.ckpt + ((int64_t)row * p.ntiles + i) * 12);
-#pragma unroll
-      for (int k = 0; k < kSections; ++k) ck[k] = carry[k];
+  if (warp < p.ntiles) warp_load(my_units, xa, xb, warp, rp, &my_full[0], lane);
+  int jt = 0;
+  for (int i = warp; i < p.ntiles; i += W, ++jt) {
+    const int st = jt & 1;
+    float* unit = my_units + (size_t)st * kUnitFloats;
+    if (i + W < p.ntiles) {
+      // the other stage was stored from one tile ago: that bulk store must have finished READING it
+      if (rp.bulk && lane == 0) tma_store_wait_read<0>();
+      warp_load(my_units + (size_t)(st ^ 1) * kUnitFloats, xa, xb, i + W, rp, &my_full[st ^ 1], lane);
     }
-    float v[kE];
+    if (rp.bulk) mbar_wait(&my_full[st], (uint32_t)((jt >> 1) & 1));
+    const int off = lane * kE;
+    const int64_t n0 = (int64_t)i * kTile + off;
+    f2 v[kE];
 #pragma unroll
-    for (int j = 0; j < kE; ++j) v[j] = (n0 + j < p.n) ? buf[j] : 0.f;
+    for (int j = 0; j < kE; ++j)
+      v[j] = (n0 + j < p.n) ? make_float2(unit[off + j], unit[kTile + off + j]) : zero2();
 
 #pragma unroll
     for (int k = 0; k < kSections; ++k) {
       const Cf c = load_cf(tb, k);
-      const float2 end = local_pass(v, c);
-      const float2 cin = scan_fwd2<W>(end, carry[k], tb, k, sm.agg + ((i * kSections + k) & 1) * 8, lane, warp);
+      const St end = local_pass(v, c);
+      St excl, tot;
+      scan_fwd(end, tb, k, so, lane, excl, tot);
+      St cin;                                                     // carry of section k entering this tile
+      if (W > 1) cin = mail.take(k, warp, jt); else cin = carry[k];
+      if (i + 1 < p.ntiles) {
+        const St cnext = mv_acc(ldm(&tb.warp[k][0]), cin, tot);   // A^(32E) c + total
+        if (W > 1) mail.put(k, (warp + 1) % W, cnext, lane); else carry[k] = cnext;
+      }
+      if (ckpt && lane == 0) ckpt[(int64_t)i * kSections + k] = make_float4(cin.s1.x, cin.s1.y, cin.s2.x, cin.s2.y);
+      const St sin = mv_acc(ldm(&tb.lane[k][lane][0]), cin, excl);    // state entering this lane's chunk
 #pragma unroll
       for (int j = 0; j < kE; ++j) {
-        const float4 m = pw_j(tb, k, j);                 // y[j] += (A^j c_in)_1
-        v[j] = fmaf(m.x, cin.x, fmaf(m.y, cin.y, v[j]));
+        const float4 t = tb.fix[k][j];                            // y[j] += (A^j s_in)_1
+        v[j] = ffma2(make_float2(t.x, t.y), sin.s1, ffma2(make_float2(t.z, t.w), sin.s2, v[j]));
       }
     }
 #pragma unroll
-    for (int j = 0; j < kE; ++j) buf[j] = v[j];
-    pipe.release(i, g, rows);
+    for (int j = 0; j < kE; ++j) { unit[off + j] = v[j].x; unit[kTile + off + j] = v[j].y; }
+    warp_store(unit, ya, yb, i, rp, lane);
   }
-  pipe.drain();
+  if (rp.bulk && lane == 0) tma_store_wait_all<0>();
 }
 
 // =============================================================================== backward
-template <int W>
+// per-warp shared memory: X[S], G[S] (row-pair units, TMA) and U1..U4 (interleaved f2, the inputs of sections 1..4);
+// the input of section 5 overwrites the G unit once dL/dy sits in registers, and dL/dx leaves through the G unit.
+template <int S>
+struct BwdUnits { static constexpr int kPerWarp = 2 * S + 4; };
+
+template <int W, int S>
 __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Smem sm(smem_raw);
-  EqTables& tb = *sm.tb;
-  __shared__ double red[W][kSections * 5];
-  const int row = blockIdx.x, item = row / p.chs;
+  using SM = Smem<W, BwdUnits<S>::kPerWarp, S>;
+  SM sm(smem_raw);
+  const PairTables& tb = *sm.tb;
+  __shared__ double red[W][kSections * 5][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tile_len = W * 32 * kE;
+  const int64_t row_a = 2 * (int64_t)blockIdx.x;
+  const bool has_b = row_a + 1 < p.rows;
+  const int64_t row_b = has_b ? row_a + 1 : row_a;
 
-  build_tables(tb, p.params + (int64_t)item * 18, p.sample_rate);
+  build_tables(*sm.tb, p.params, row_a / p.chs, row_b / p.chs, p.sample_rate);
+  Mail<W> mail{sm.mail_data, sm.mail_bar};
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S * W; ++i) mbar_init(&sm.full[i], 1);
+    if (W > 1) mail.init_all(); else fence_barrier_init();
+  }
+  __syncthreads();
 
-  TileGeom g{p.n, tile_len, p.ntiles, true};
-  RowIOBwd rows{p.x + (int64_t)row * p.n, p.gy + (int64_t)row * p.n, p.y + (int64_t)row * p.n};
-  TilePipe<kStages> pipe;
-  pipe.init(sm.bars, sm.stages, 2, tile_len, p.bulk != 0);
-  pipe.prologue(g, rows);
-  // thread-private scratch for the inputs of sections 1..5 (u_1..u_5), behind the pipeline stages
-  float* scratch = sm.stages + (size_t)kStages * 2 * tile_len;
+  const RowPair rp{p.n, p.ntiles, p.bulk != 0, has_b};
+  const float* xa = p.x + row_a * p.n;
+  const float* xb = p.x + row_b * p.n;
+  const float* ga = p.gy + row_a * p.n;
+  const float* gb = p.gy + row_b * p.n;
+  float* oa = p.y + row_a * p.n;
+  float* ob = p.y + row_b * p.n;
+  float* my = sm.units + (size_t)warp * BwdUnits<S>::kPerWarp * kUnitFloats;
+  float* X = my;                                   // [S] units
+  float* G = my + (size_t)S * kUnitFloats;         // [S] units
+  f2* U = reinterpret_cast<f2*>(my + (size_t)2 * S * kUnitFloats);     // [4][kTile] f2: inputs of sections 1..4
+  uint64_t* my_full = sm.full + warp * S;
+  const StepOffsets so_f = fwd_offsets(lane), so_r = rev_offsets(lane);
+  const float4* ckpt = reinterpret_cast<const float4*>(p.ckpt) + (int64_t)blockIdx.x * p.ntiles * kSections;
 
-  float2 adj[kSections];          // adjoint state at the first sample of the next tile, per section
-  float acc[kSections][5];
+  St adj[kSections];                               // W == 1: adjoint carries in registers
+  f2 acc[kSections][5];
 #pragma unroll
   for (int k = 0; k < kSections; ++k) {
-    adj[k] = make_float2(0.f, 0.f);
+    adj[k] = {zero2(), zero2()};
 #pragma unroll
-    for (int q = 0; q < 5; ++q) acc[k][q] = 0.f;
+    for (int q = 0; q < 5; ++q) acc[k][q] = zero2();
   }
-  const int off = threadIdx.x * kE;
 
-  for (int i = 0; i < p.ntiles; ++i) {
-    pipe.acquire(i, g, rows);
-    const int st = i % kStages;
-    const int tile = g.tile_of(i);
-    const int64_t n0 = (int64_t)tile * tile_len + off;
-    const float* xb = pipe.buf(st, 0) + off;
-    float* gb = pipe.buf(st, 1) + off;
-    const float2* ck = reinterpret_cast<const float2*>(p.ckpt + ((int64_t)row * p.ntiles + tile) * 12);
+  auto load_seq = [&](int seq, int stage) {        // x and dL/dy tiles of sequence number seq complete on ONE barrier
+    const int tile = p.ntiles - 1 - seq;
+    const int64_t pos = (int64_t)tile * kTile;
+    const int len = rp.len_of(tile);
+    float* xu = X + (size_t)stage * kUnitFloats;
+    float* gu = G + (size_t)stage * kUnitFloats;
+    if (rp.bulk) {
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&my_full[stage], (uint32_t)len * 16u);
+        tma_load_1d(xu, xa + pos, (uint32_t)len * 4u, &my_full[stage]);
+        tma_load_1d(xu + kTile, xb + pos, (uint32_t)len * 4u, &my_full[stage]);
+        tma_load_1d(gu, ga + pos, (uint32_t)len * 4u, &my_full[stage]);
+        tma_load_1d(gu + kTile, gb + pos, (uint32_t)len * 4u, &my_full[stage]);
+      }
+    } else {
+      for (int i = lane; i < len; i += 32) {
+        xu[i] = xa[pos + i]; xu[kTile + i] = xb[pos + i];
+        gu[i] = ga[pos + i]; gu[kTile + i] = gb[pos + i];
+      }
+      __syncwarp();
+    }
+  };
 
-    // ---- phase F: recompute the section inputs u_1..u_5 and every section's incoming state ----
-    float2 cin[kSections];
-    {
-      float v[kE];
+  if (S > 1 && warp < p.ntiles) load_seq(warp, 0);
+  int jt = 0;
+  for (int seq = warp; seq < p.ntiles; seq += W, ++jt) {
+    const int st = (S > 1) ? (jt & 1) : 0;
+    const int tile = p.ntiles - 1 - seq;
+    if (S > 1) {
+      if (seq + W < p.ntiles) {
+        if (rp.bulk && lane == 0) tma_store_wait_read<0>();      // the store that left from G[st ^ 1] one tile ago
+        load_seq(seq + W, st ^ 1);
+      }
+    } else {
+      if (rp.bulk && lane == 0) tma_store_wait_read<0>();
+      __syncwarp();
+      load_seq(seq, 0);
+    }
+    if (rp.bulk) mbar_wait(&my_full[st], (uint32_t)(((S > 1) ? (jt >> 1) : jt) & 1));
+    const float* xu = X + (size_t)st * kUnitFloats;
+    float* gu = G + (size_t)st * kUnitFloats;
+    f2* U5 = reinterpret_cast<f2*>(gu);            // input of section 5, interleaved, over the consumed dL/dy unit
+    const int off = lane * kE;
+    const int64_t n0 = (int64_t)tile * kTile + off;
+
+    f2 gq[kE];                                     // dL/dy of the lane's samples; becomes dL/du_k section by section
 #pragma unroll
-      for (int j = 0; j < kE; ++j) v[j] = (n0 + j < p.n) ? xb[j] : 0.f;
+    for (int j = 0; j < kE; ++j)
+      gq[j] = (n0 + j < p.n) ? make_float2(gu[off + j], gu[kTile + off + j]) : zero2();
+    __syncwarp();                                  // all lanes hold their dL/dy before the unit is overwritten
+
+    // ---- phase F: recompute the section inputs u_1..u_5 and every section's state entering the lane's chunk ----
+    St sin[kSections];
+    {
+      f2 v[kE];
+#pragma unroll
+      for (int j = 0; j < kE; ++j)
+        v[j] = (n0 + j < p.n) ? make_float2(xu[off + j], xu[kTile + off + j]) : zero2();
 #pragma unroll
       for (int k = 0; k < kSections; ++k) {
         const Cf c = load_cf(tb, k);
-        const float2 end = local_pass(v, c);
-        float2 ct = ck[k];
-        cin[k] = scan_fwd2<W>(end, ct, tb, k, sm.agg + (2 * k + 0) * 8, lane, warp);
+        const St end = local_pass(v, c);
+        St excl, tot;
+        scan_fwd(end, tb, k, so_f, lane, excl, tot);
+        const float4 ck = ckpt[(int64_t)tile * kSections + k];
+        const St cin = {make_float2(ck.x, ck.y), make_float2(ck.z, ck.w)};
+        sin[k] = mv_acc(ldm(&tb.lane[k][lane][0]), cin, excl);
         if (k < kSections - 1) {
-          float* uk = scratch + (size_t)k * tile_len + off;
+          f2* uk = (k == kSections - 2) ? U5 + off : U + (size_t)k * kTile + off;
 #pragma unroll
           for (int j = 0; j < kE; ++j) {
-            const float4 m = pw_j(tb, k, j);
-            v[j] = fmaf(m.x, cin[k].x, fmaf(m.y, cin[k].y, v[j]));
+            const float4 t = tb.fix[k][j];
+            v[j] = ffma2(make_float2(t.x, t.y), sin[k].s1, ffma2(make_float2(t.z, t.w), sin[k].s2, v[j]));
             uk[j] = v[j];
           }
         }
@@ -434,78 +621,92 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
     }
 
     // ---- phase B: unwind the sections 6 -> 1 ----
-    float gq[kE];
-#pragma unroll
-    for (int j = 0; j < kE; ++j) gq[j] = (n0 + j < p.n) ? gb[j] : 0.f;
 #pragma unroll
     for (int k = kSections - 1; k >= 0; --k) {
       const Cf c = load_cf(tb, k);
-      float u[kE], s1[kE], s2[kE];
-      {
-        const float* uk = (k == 0) ? xb : (scratch + (size_t)(k - 1) * tile_len + off);
+      f2 u[kE], s1[kE], s2[kE];
+      if (k == 0) {
 #pragma unroll
-        for (int j = 0; j < kE; ++j) u[j] = (n0 + j < p.n) ? uk[j] : 0.f;
+        for (int j = 0; j < kE; ++j)
+          u[j] = (n0 + j < p.n) ? make_float2(xu[off + j], xu[kTile + off + j]) : zero2();
+      } else {
+        const f2* uk = (k == kSections - 1) ? U5 + off : U + (size_t)(k - 1) * kTile + off;
+#pragma unroll
+        for (int j = 0; j < kE; ++j) u[j] = uk[j];
       }
       {  // true-state forward pass: s[j] = state BEFORE sample j
-        float a1 = cin[k].x, a2 = cin[k].y;
+        f2 a1 = sin[k].s1, a2 = sin[k].s2;
 #pragma unroll
         for (int j = 0; j < kE; ++j) {
           s1[j] = a1; s2[j] = a2;
-          const float t1 = fmaf(c.be1, u[j], fmaf(c.sg, a1, a2));
-          a2 = fmaf(c.B2, u[j], fmaf(c.q, a1, c.sg * a2));
-          a1 = t1;
+          const f2 ta = ffma2(c.be1, u[j], a2);
+          const f2 tb2 = ffma2(c.q, a1, fmul2(c.B2, u[j]));
+          a1 = ffma2(c.sg, a1, ta);
+          a2 = ffma2(c.sg, a2, tb2);
         }
       }
-      float2 agg_v;
+      St agg_v;
       {  // zero-terminal reverse pass: only the value reaching the chunk's first sample is needed
-        float l1 = 0.f, l2 = 0.f;
+        f2 l1 = zero2(), l2 = zero2();
 #pragma unroll
         for (int j = kE - 1; j >= 0; --j) {
-          const float t1 = fmaf(c.sg, l1, fmaf(c.q, l2, gq[j]));
-          l2 = fmaf(c.sg, l2, l1);
+          const f2 t1 = ffma2(c.sg, l1, ffma2(c.q, l2, gq[j]));
+          l2 = ffma2(c.sg, l2, l1);
           l1 = t1;
         }
-        agg_v = make_float2(l1, l2);
+        agg_v = {l1, l2};
       }
-      const float2 din = scan_rev2<W>(agg_v, adj[k], tb, k, sm.agg + (2 * k + 1) * 8, lane, warp);
+      St excl, tot;
+      scan_rev(agg_v, tb, k, so_r, lane, excl, tot);
+      St ain;                                      // adjoint state at the first sample of the NEXT tile (in time)
+      if (W > 1) ain = mail.take(k, warp, jt); else ain = adj[k];
+      if (seq + 1 < p.ntiles) {
+        const St anext = mtv_acc(ldm(&tb.warp[k][0]), ain, tot);
+        if (W > 1) mail.put(k, (warp + 1) % W, anext, lane); else adj[k] = anext;
+      }
+      // distance from the first sample of lane+1's chunk to the first sample of the next tile: (31-lane) chunks
+      const St din = mtv_acc(ldm(&tb.lane[k][31 - lane][0]), ain, excl);
       {  // final reverse pass with the true terminal adjoint state
-        float l1 = din.x, l2 = din.y;      // lambda[n+1] while processing sample n
+        f2 l1 = din.s1, l2 = din.s2;               // lambda[n+1] while processing sample n
 #pragma unroll
         for (int j = kE - 1; j >= 0; --j) {
-          const float gj = gq[j];
-          acc[k][0] = fmaf(l1, s1[j], fmaf(l2, s2[j], acc[k][0]));
-          acc[k][1] = fmaf(l2, s1[j], acc[k][1]);
-          acc[k][2] = fmaf(l1, u[j], acc[k][2]);
-          acc[k][3] = fmaf(l2, u[j], acc[k][3]);
-          acc[k][4] = fmaf(gj, u[j], acc[k][4]);
-          gq[j] = fmaf(c.be1, l1, fmaf(c.B2, l2, c.b0 * gj));
-          const float t1 = fmaf(c.sg, l1, fmaf(c.q, l2, gj));
-          l2 = fmaf(c.sg, l2, l1);
+          const f2 gj = gq[j];
+          acc[k][0] = ffma2(l1, s1[j], ffma2(l2, s2[j], acc[k][0]));
+          acc[k][1] = ffma2(l2, s1[j], acc[k][1]);
+          acc[k][2] = ffma2(l1, u[j], acc[k][2]);
+          acc[k][3] = ffma2(l2, u[j], acc[k][3]);
+          acc[k][4] = ffma2(gj, u[j], acc[k][4]);
+          gq[j] = ffma2(c.be1, l1, ffma2(c.B2, l2, fmul2(c.b0, gj)));
+          const f2 t1 = ffma2(c.sg, l1, ffma2(c.q, l2, gj));
+          l2 = ffma2(c.sg, l2, l1);
           l1 = t1;
         }
       }
+      if (k == kSections - 1) __syncwarp();        // every lane has read its u_5 before dL/dx may land in the G unit
     }
 #pragma unroll
-    for (int j = 0; j < kE; ++j) gb[j] = gq[j];
-    pipe.release(i, g, rows);
+    for (int j = 0; j < kE; ++j) { gu[off + j] = gq[j].x; gu[kTile + off + j] = gq[j].y; }
+    warp_store(gu, oa, ob, tile, rp, lane);
   }
-  pipe.drain();
+  if (rp.bulk && lane == 0) tma_store_wait_all<0>();
 
-  // ---- deterministic block reduction of the 30 sums (fp64), one partial row per CTA ----
+  // ---- deterministic block reduction of the 2 x 30 sums (fp64), one partial row per row of the pair ----
 #pragma unroll
   for (int k = 0; k < kSections; ++k) {
 #pragma unroll
     for (int q = 0; q < 5; ++q) {
-      const double s = warp_sum((double)acc[k][q]);
-      if (lane == 0) red[warp][k * 5 + q] = s;
+      const double sa = warp_sum((double)acc[k][q].x), sb = warp_sum((double)acc[k][q].y);
+      if (lane == 0) { red[warp][k * 5 + q][0] = sa; red[warp][k * 5 + q][1] = sb; }
     }
   }
   __syncthreads();
-  if (threadIdx.x < kSections * 5) {
+  if (threadIdx.x < kSections * 5 * 2) {
+    const int h = threadIdx.x / (kSections * 5), e = threadIdx.x - h * (kSections * 5);
     double s = 0.0;
 #pragma unroll
-    for (int w = 0; w < W; ++w) s += red[w][threadIdx.x];
-    p.partial[(int64_t)row * 30 + threadIdx.x] = (float)s;
+    for (int w = 0; w < W; ++w) s += red[w][e][h];
+    if (h == 0) p.partial[row_a * 30 + e] = (float)s;
+    else if (has_b) p.partial[row_b * 30 + e] = (float)s;
   }
 }
 
@@ -534,29 +735,64 @@ __global__ void eq_param_grad_kernel(const float* __restrict__ partial, const fl
 }
 
 // ---- host side -----------------------------------------------------------------------------
-int pick_warps(int64_t rows) {
-  if (debug_forced_warps()) return debug_forced_warps() > 4 ? 4 : debug_forced_warps();
-  const int64_t want = (int64_t)DASP_EQ_WARPS_PER_SM * sm_count();
+#ifndef DASP_EQ_FWD_WARPS_PER_SM
+#define DASP_EQ_FWD_WARPS_PER_SM 12
+#endif
+#ifndef DASP_EQ_BWD_WARPS_PER_SM
+#define DASP_EQ_BWD_WARPS_PER_SM 8
+#endif
+// experiment knobs (read once): DASP_EQ_FWD_W / DASP_EQ_BWD_W = warps per row pair, DASP_EQ_BWD_S = stages of the
+// backward's x / dL/dy units.  0 / unset = automatic.
+int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
+}
+int tune_fwd_w() { static const int v = env_int("DASP_EQ_FWD_W"); return v; }
+int tune_bwd_w() { static const int v = env_int("DASP_EQ_BWD_W"); return v; }
+int tune_bwd_s() {
+  static const int v = env_int("DASP_EQ_BWD_S");
+  return debug_eq_bwd_stages() ? debug_eq_bwd_stages() : v;
+}
+
+// warps per row pair: enough warps per SM to hide the scan/shuffle latency, never more than 8
+int pick_warps(int64_t pairs, int want_per_sm, int max_w, int tuned) {
+  const int f = debug_forced_warps() ? debug_forced_warps() : tuned;
+  if (f == 1 || f == 2 || f == 4 || f == 8) return f > max_w ? max_w : f;
+  const int64_t want = (int64_t)want_per_sm * sm_count();
   int w = 1;
-  while (w < 4 && rows * w < want) w *= 2;
+  while (w < max_w && pairs * w < want) w *= 2;
   return w;
 }
-size_t smem_fwd(int w) { return kHdr + (size_t)kStages * 1 * (w * 32 * kE) * 4; }
-size_t smem_bwd(int w) { return kHdr + (size_t)(kStages * 2 + (kSections - 1)) * (w * 32 * kE) * 4; }
+
+// one-off opt-in to > 48 KB dynamic shared memory, cached per (device, kernel)
+template <class K>
+int ensure_smem(K kernel, size_t bytes) {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  DASP_CUDA_OK(cudaGetDevice(&dev));
+  if (done_dev != dev) {
+    DASP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    done_dev = dev;
+  }
+  return DASP_OK;
+}
 
 template <int W>
-int launch_fwd_w(const EqParams& p, int64_t rows, cudaStream_t st) {
-  const size_t smem = smem_fwd(W);
-  DASP_CUDA_OK(cudaFuncSetAttribute(eq_fwd_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  eq_fwd_kernel<W><<<(unsigned)rows, W * 32, smem, st>>>(p);
+int launch_fwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
+  constexpr size_t smem = Smem<W, kFwdStages, kFwdStages>::kBytes;
+  int rc = ensure_smem(eq_fwd_kernel<W>, smem);
+  if (rc != DASP_OK) return rc;
+  eq_fwd_kernel<W><<<(unsigned)pairs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("eq_fwd_kernel");
   return DASP_OK;
 }
-template <int W>
-int launch_bwd_w(const EqParams& p, int64_t rows, cudaStream_t st) {
-  const size_t smem = smem_bwd(W);
-  DASP_CUDA_OK(cudaFuncSetAttribute(eq_bwd_kernel<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  eq_bwd_kernel<W><<<(unsigned)rows, W * 32, smem, st>>>(p);
+template <int W, int S>
+int launch_bwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
+  constexpr size_t smem = Smem<W, BwdUnits<S>::kPerWarp, S>::kBytes;
+  static_assert(smem <= 227 * 1024, "backward variant does not fit in shared memory");
+  int rc = ensure_smem(eq_bwd_kernel<W, S>, smem);
+  if (rc != DASP_OK) return rc;
+  eq_bwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("eq_bwd_kernel");
   return DASP_OK;
 }
@@ -568,7 +804,11 @@ using namespace dasp;
 
 extern "C" {
 
-int64_t dasp_eq_tile_len(int64_t rows) { return (int64_t)pick_warps(rows) * 32 * kE; }
+int64_t dasp_eq_tile_len(int64_t rows) { (void)rows; return kTile; }
+int64_t dasp_eq_ckpt_floats(int64_t bs, int64_t chs, int64_t n) {
+  const int64_t pairs = (bs * chs + 1) / 2, ntiles = (n + kTile - 1) / kTile;
+  return pairs * (ntiles > 0 ? ntiles : 1) * kSections * 4;
+}
 int64_t dasp_eq_bwd_workspace_floats(int64_t bs, int64_t chs) { return bs * chs * 30; }
 
 int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int64_t bs, int64_t chs, int64_t n,
@@ -578,19 +818,19 @@ int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int6
   if (bs == 0 || n == 0) return DASP_OK;
   DASP_REQUIRE(x && params && y, "eq fwd: null pointer");
   DASP_REQUIRE(sample_rate > 0.f, "eq fwd: sample_rate must be positive");
-  const int64_t rows = bs * chs;
-  DASP_REQUIRE(rows < (1ll << 31), "eq fwd: too many rows");
-  const int w = pick_warps(rows);
-  const int tile_len = w * 32 * kE;
+  const int64_t rows = bs * chs, pairs = (rows + 1) / 2;
+  DASP_REQUIRE(pairs < (1ll << 31), "eq fwd: too many rows");
+  const int w = pick_warps(pairs, DASP_EQ_FWD_WARPS_PER_SM, 8, tune_fwd_w());
   EqParams p{};
-  p.x = x; p.y = y; p.params = params; p.ckpt = ckpt; p.n = n; p.chs = (int)chs;
-  p.ntiles = (int)((n + tile_len - 1) / tile_len); p.sample_rate = sample_rate;
+  p.x = x; p.y = y; p.params = params; p.ckpt = ckpt; p.n = n; p.rows = rows; p.chs = (int)chs;
+  p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;
   p.bulk = (n % 4 == 0) && aligned16(x) && aligned16(y);
   cudaStream_t st = (cudaStream_t)stream;
   switch (w) {
-    case 1: return launch_fwd_w<1>(p, rows, st);
-    case 2: return launch_fwd_w<2>(p, rows, st);
-    default: return launch_fwd_w<4>(p, rows, st);
+    case 1: return launch_fwd_w<1>(p, pairs, st);
+    case 2: return launch_fwd_w<2>(p, pairs, st);
+    case 4: return launch_fwd_w<4>(p, pairs, st);
+    default: return launch_fwd_w<8>(p, pairs, st);
   }
 }
 
@@ -604,23 +844,27 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
   DASP_REQUIRE(gparams != nullptr, "eq bwd: null gparams");
   if (n == 0) { DASP_CUDA_OK(cudaMemsetAsync(gparams, 0, sizeof(float) * 18 * bs, st)); return DASP_OK; }
   DASP_REQUIRE(gy && x && params && ckpt && gx, "eq bwd: null pointer");
-  const int64_t rows = bs * chs;
-  DASP_REQUIRE(rows < (1ll << 31), "eq bwd: too many rows");
+  const int64_t rows = bs * chs, pairs = (rows + 1) / 2;
+  DASP_REQUIRE(pairs < (1ll << 31), "eq bwd: too many rows");
   if (ws == nullptr || ws_floats < rows * 30) {
     set_error("eq bwd: workspace needs %lld floats, got %lld", (long long)(rows * 30), (long long)ws_floats);
     return DASP_ERR_WORKSPACE;
   }
-  const int w = pick_warps(rows);
-  const int tile_len = w * 32 * kE;
+  const int w = pick_warps(pairs, DASP_EQ_BWD_WARPS_PER_SM, 8, tune_bwd_w());
+  const int stages = (w == 8) ? 1 : (tune_bwd_s() == 1 ? 1 : 2);
   EqParams p{};
   p.x = x; p.gy = gy; p.y = gx; p.params = params; p.ckpt = const_cast<float*>(ckpt); p.partial = ws; p.n = n;
-  p.chs = (int)chs; p.ntiles = (int)((n + tile_len - 1) / tile_len); p.sample_rate = sample_rate;
+  p.rows = rows; p.chs = (int)chs; p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;
   p.bulk = (n % 4 == 0) && aligned16(x) && aligned16(gy) && aligned16(gx);
   int rc;
-  switch (w) {
-    case 1: rc = launch_bwd_w<1>(p, rows, st); break;
-    case 2: rc = launch_bwd_w<2>(p, rows, st); break;
-    default: rc = launch_bwd_w<4>(p, rows, st); break;
+  switch (w * 10 + stages) {
+    case 11: rc = launch_bwd_w<1, 1>(p, pairs, st); break;
+    case 12: rc = launch_bwd_w<1, 2>(p, pairs, st); break;
+    case 21: rc = launch_bwd_w<2, 1>(p, pairs, st); break;
+    case 22: rc = launch_bwd_w<2, 2>(p, pairs, st); break;
+    case 41: rc = launch_bwd_w<4, 1>(p, pairs, st); break;
+    case 42: rc = launch_bwd_w<4, 2>(p, pairs, st); break;
+    default: rc = launch_bwd_w<8, 1>(p, pairs, st); break;
   }
   if (rc != DASP_OK) return rc;
   const int64_t tot = bs * kSections;

@@ -58,6 +58,8 @@ int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 // Test hook (dasp_debug_force_warps): 0 = automatic; 1/2/4/8 pins the warps-per-row choice of the scan kernels
 // so that every kernel variant can be exercised at small, cheap-to-check batch sizes.
 int debug_forced_warps();
+// Test hook (dasp_debug_eq_bwd_stages): 0 = automatic; 1 / 2 pins the number of x / dL/dy stages of the EQ backward
+int debug_eq_bwd_stages();
 // Test hook (dasp_debug_reverb_path): IR synthesis of the device-noise reverb: 0 = automatic, 1 = generator / cuFFT /
 // shaping kernels, 2 = single cluster kernel
 int debug_reverb_path();
@@ -104,6 +106,10 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+// plain arrive (release semantics at CTA scope): completes one pending arrival of the current phase
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(

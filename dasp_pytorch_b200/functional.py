@@ -428,8 +428,7 @@ class _ParametricEqFn(torch.autograd.Function):
         ckpt = None
         with torch.cuda.device(x.device):
             if need_bwd:
-                tile = lib.dasp_eq_tile_len(bs * chs)
-                ckpt = torch.empty(bs * chs * max(1, -(-n // tile)) * 12, dtype=torch.float32, device=x.device)
+                ckpt = torch.empty(max(1, lib.dasp_eq_ckpt_floats(bs, chs, n)), dtype=torch.float32, device=x.device)
             with _timed("eq_fwd", x.device):
                 check(lib.dasp_eq_fwd(ptr(x), ptr(params), ptr(y), ptr(ckpt), bs, chs, n, float(sample_rate),
                                       stream_ptr(x.device)), "dasp_eq_fwd")

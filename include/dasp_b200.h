@@ -47,6 +47,8 @@ void dasp_shutdown(void);
  * callers (they exist so that every kernel variant can be pinned against the oracle at small sizes). */
 /* test hook: pin the warps-per-row variant of the scan kernels (1, 2, 4, 8; 0 = automatic choice) */
 void dasp_debug_force_warps(int warps);
+/* test hook: pin the number of x / dL/dy stages per warp of the EQ backward (1 or 2; 0 = automatic) */
+void dasp_debug_eq_bwd_stages(int stages);
 /* test hook, IR synthesis of the device-noise reverb (all variants draw the same Philox stream and must agree):
    0 = automatic (generator -> fused in-shared-memory inverse FFT + shaping kernel when the block FFT is 8192 points),
    1 = generator -> batched cuFFT -> shaping kernel, 2 = one thread-block-cluster kernel per item */
@@ -122,10 +124,12 @@ int dasp_dynamics_bwd(int kind, const float* gy, const float* x, const float* th
  *      signal.biquad signal.py:242-306 and signal.sosfilt_via_fsm signal.py:136-166) ------
  * params is [bs][18] = (gain_dB, cutoff_Hz, Q) for low shelf, band0..band3, high shelf, i.e. the
  * 18 tensors of the reference signature stacked in order; the same filter is applied to every
- * channel of an item (signal.py:157-158).  ckpt (fwd: optional out, bwd: in) holds the twelve
- * section states at every tile boundary: bs*chs * ceil(n / dasp_eq_tile_len(bs*chs)) * 12 floats.
- * gparams is [bs][18]; ws needs dasp_eq_bwd_workspace_floats(bs, chs) floats. */
+ * channel of an item (signal.py:157-158).  Rows (item, channel) are processed in pairs; ckpt (fwd: optional out,
+ * bwd: in) holds the section states of a pair at every tile boundary: dasp_eq_ckpt_floats(bs, chs, n) floats
+ * (tiles of dasp_eq_tile_len() samples).  gparams is [bs][18]; ws needs dasp_eq_bwd_workspace_floats(bs, chs)
+ * floats. */
 int64_t dasp_eq_tile_len(int64_t rows);
+int64_t dasp_eq_ckpt_floats(int64_t bs, int64_t chs, int64_t n);
 int64_t dasp_eq_bwd_workspace_floats(int64_t bs, int64_t chs);
 int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int64_t bs, int64_t chs,
                 int64_t n, float sample_rate, void* stream);

@@ -71,17 +71,43 @@ def test_eq_ragged_shapes(cuda_device, bs, chs, n):
     _check(cuda_device, x, denorm(p01, eq_ranges()), tail=1 << 16)
 
 
-@pytest.mark.parametrize("warps", [1, 2, 4])
-def test_eq_every_warps_per_row_variant(cuda_device, warps):
-    """the kernels pick 1/2/4 warps per row from the batch size; pin each variant (test hook) on a small batch
-    with several tiles and a ragged tail so that all three run at a size the oracle checks in seconds"""
+@pytest.mark.parametrize("warps,stages", [(1, 1), (1, 2), (2, 1), (2, 2), (4, 1), (4, 2), (8, 1)])
+def test_eq_every_warps_per_pair_variant(cuda_device, warps, stages):
+    """the kernels pick 1/2/4/8 warps per row pair from the batch size (warp w owns tiles w, w+W, ...; carries travel
+    through mbarrier-guarded mailboxes) and 1 or 2 load stages in the backward; pin each variant (test hooks) on a
+    small batch with many tiles per warp, a ragged tail and an odd number of rows, so that every instantiation runs
+    at a size the oracle checks in seconds"""
     from dasp_pytorch_b200 import _abi
-    x, p01 = _inputs(3, 2, 480 * 4 * 2 + 100, seed=14, low_corner=(warps == 2))
+    x, p01 = _inputs(3, 1 if warps == 4 else 2, 480 * 8 * 3 + 100, seed=14, low_corner=(warps == 2))
     _abi.lib().dasp_debug_force_warps(warps)
+    _abi.lib().dasp_debug_eq_bwd_stages(stages)
     try:
         _check(cuda_device, x, denorm(p01, eq_ranges()), tail=1 << 16, strict=True)
     finally:
         _abi.lib().dasp_debug_force_warps(0)
+        _abi.lib().dasp_debug_eq_bwd_stages(0)
+
+
+def test_eq_is_deterministic_and_warp_count_invariant(cuda_device):
+    """same inputs -> bit-identical outputs run to run (no atomics, fixed reduction order), and the result does not
+    depend on how many warps share a row (the carries are the same numbers whichever warp computes them)"""
+    import dasp_pytorch_b200 as D
+    from dasp_pytorch_b200 import _abi
+    x, p01 = _inputs(4, 2, 480 * 9 + 36, seed=21)
+    xs = x.to(cuda_device)
+    ps = [p.to(cuda_device) for p in denorm(p01, eq_ranges())]
+    outs = []
+    for w in (1, 2, 4, 8, 2):
+        _abi.lib().dasp_debug_force_warps(w)
+        try:
+            xx = xs.clone().requires_grad_(True)
+            y = D.parametric_eq(xx, SR, *ps)
+            y.pow(2).mean().backward()
+            outs.append((y.detach().clone(), xx.grad.clone()))
+        finally:
+            _abi.lib().dasp_debug_force_warps(0)
+    for y, g in outs[1:]:
+        assert torch.equal(y, outs[0][0]) and torch.equal(g, outs[0][1])
 
 
 def test_eq_other_sample_rates_and_param_forms(cuda_device):
