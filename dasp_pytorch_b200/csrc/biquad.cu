@@ -61,7 +61,9 @@ constexpr int kE = DASP_EQ_E;    // samples per lane per tile (odd: conflict-fre
 static_assert(kE % 2 == 1, "E must be odd");
 constexpr int kTile = 32 * kE;   // samples per tile (one warp)
 constexpr int kSections = 6;
-constexpr int kFwdStages = 2;
+#ifndef DASP_EQ_FWD_REGS
+#define DASP_EQ_FWD_REGS 90      // registers per thread of eq_fwd_kernel (ptxas -v), for the occupancy-aware choice of W
+#endif
 
 // ------------------------------------------------------------------ coefficient design (fp64)
 // forward-mode dual number with 3 directional derivatives (gain_dB, fc, Q)
@@ -413,8 +415,9 @@ struct Smem {
 };
 
 // =============================================================================== forward
-template <int W>
+template <int W, int S>
 __global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
+  constexpr int kFwdStages = S;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   using SM = Smem<W, kFwdStages, kFwdStages>;
   SM sm(smem_raw);
@@ -446,23 +449,34 @@ __global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
 #pragma unroll
   for (int k = 0; k < kSections; ++k) carry[k] = {zero2(), zero2()};
 
-  if (warp < p.ntiles) warp_load(my_units, xa, xb, warp, rp, &my_full[0], lane);
+  if (S > 1 && warp < p.ntiles) warp_load(my_units, xa, xb, warp, rp, &my_full[0], lane);
   int jt = 0;
   for (int i = warp; i < p.ntiles; i += W, ++jt) {
-    const int st = jt & 1;
+    const int st = (S > 1) ? (jt & 1) : 0;
     float* unit = my_units + (size_t)st * kUnitFloats;
-    if (i + W < p.ntiles) {
-      // the other stage was stored from one tile ago: that bulk store must have finished READING it
+    if (S > 1) {
+      if (i + W < p.ntiles) {
+        // the other stage was stored from one tile ago: that bulk store must have finished READING it
+        if (rp.bulk && lane == 0) tma_store_wait_read<0>();
+        warp_load(my_units + (size_t)(st ^ 1) * kUnitFloats, xa, xb, i + W, rp, &my_full[st ^ 1], lane);
+      }
+    } else {
       if (rp.bulk && lane == 0) tma_store_wait_read<0>();
-      warp_load(my_units + (size_t)(st ^ 1) * kUnitFloats, xa, xb, i + W, rp, &my_full[st ^ 1], lane);
+      __syncwarp();
+      warp_load(unit, xa, xb, i, rp, &my_full[0], lane);
     }
-    if (rp.bulk) mbar_wait(&my_full[st], (uint32_t)((jt >> 1) & 1));
+    if (rp.bulk) mbar_wait(&my_full[st], (uint32_t)(((S > 1) ? (jt >> 1) : jt) & 1));
     const int off = lane * kE;
     const int64_t n0 = (int64_t)i * kTile + off;
     f2 v[kE];
+    if ((int64_t)(i + 1) * kTile <= p.n) {           // whole tile inside the row (warp-uniform): no per-sample masks
 #pragma unroll
-    for (int j = 0; j < kE; ++j)
-      v[j] = (n0 + j < p.n) ? make_float2(unit[off + j], unit[kTile + off + j]) : zero2();
+      for (int j = 0; j < kE; ++j) v[j] = make_float2(unit[off + j], unit[kTile + off + j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kE; ++j)
+        v[j] = (n0 + j < p.n) ? make_float2(unit[off + j], unit[kTile + off + j]) : zero2();
+    }
 
 #pragma unroll
     for (int k = 0; k < kSections; ++k) {
@@ -700,8 +714,8 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
     }
   }
   __syncthreads();
-  if (threadIdx.x < kSections * 5 * 2) {
-    const int h = threadIdx.x / (kSections * 5), e = threadIdx.x - h * (kSections * 5);
+  for (int o = threadIdx.x; o < kSections * 5 * 2; o += W * 32) {      // W = 1 has fewer threads than outputs
+    const int h = o / (kSections * 5), e = o - h * (kSections * 5);
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < W; ++w) s += red[w][e][h];
@@ -735,12 +749,6 @@ __global__ void eq_param_grad_kernel(const float* __restrict__ partial, const fl
 }
 
 // ---- host side -----------------------------------------------------------------------------
-#ifndef DASP_EQ_FWD_WARPS_PER_SM
-#define DASP_EQ_FWD_WARPS_PER_SM 12
-#endif
-#ifndef DASP_EQ_BWD_WARPS_PER_SM
-#define DASP_EQ_BWD_WARPS_PER_SM 8
-#endif
 // experiment knobs (read once): DASP_EQ_FWD_W / DASP_EQ_BWD_W = warps per row pair, DASP_EQ_BWD_S = stages of the
 // backward's x / dL/dy units.  0 / unset = automatic.
 int env_int(const char* name) {
@@ -748,20 +756,32 @@ int env_int(const char* name) {
   return v ? atoi(v) : 0;
 }
 int tune_fwd_w() { static const int v = env_int("DASP_EQ_FWD_W"); return v; }
+int tune_fwd_s() { static const int v = env_int("DASP_EQ_FWD_S"); return v; }
 int tune_bwd_w() { static const int v = env_int("DASP_EQ_BWD_W"); return v; }
 int tune_bwd_s() {
   static const int v = env_int("DASP_EQ_BWD_S");
   return debug_eq_bwd_stages() ? debug_eq_bwd_stages() : v;
 }
 
-// warps per row pair: enough warps per SM to hide the scan/shuffle latency, never more than 8
-int pick_warps(int64_t pairs, int want_per_sm, int max_w, int tuned) {
+// Warps per row pair.  All pairs should be resident at once (one wave: a second, partly filled wave costs more than a
+// few extra warps gain), so with c = ceil(pairs / SMs) CTAs per SM the largest W whose shared memory (and register
+// file share) still allows c CTAs per SM is taken; W in {1, 2, 3, 4, 6, 8}.
+constexpr int kWarpChoices[6] = {1, 2, 3, 4, 6, 8};
+constexpr size_t kSmemPerSm = 227 * 1024, kSmemCtaReserve = 1024;
+template <class SmemBytes>
+int pick_warps(int64_t pairs, int regs_per_thread, int tuned, SmemBytes smem_of) {
   const int f = debug_forced_warps() ? debug_forced_warps() : tuned;
-  if (f == 1 || f == 2 || f == 4 || f == 8) return f > max_w ? max_w : f;
-  const int64_t want = (int64_t)want_per_sm * sm_count();
-  int w = 1;
-  while (w < max_w && pairs * w < want) w *= 2;
-  return w;
+  for (int c : kWarpChoices) if (f == c) return f;
+  const int64_t sms = sm_count();
+  int64_t per_sm = (pairs + sms - 1) / sms;
+  if (per_sm < 1) per_sm = 1;
+  int best = 1;
+  for (int w : kWarpChoices) {
+    const bool fits_smem = (smem_of(w) + kSmemCtaReserve) * (size_t)per_sm <= kSmemPerSm;
+    const bool fits_regs = (int64_t)regs_per_thread * 32 * w * per_sm <= 65536;
+    if (fits_smem && fits_regs && w * per_sm <= 64) best = w;
+  }
+  return best;
 }
 
 // one-off opt-in to > 48 KB dynamic shared memory, cached per (device, kernel)
@@ -777,18 +797,39 @@ int ensure_smem(K kernel, size_t bytes) {
   return DASP_OK;
 }
 
-template <int W>
+constexpr size_t fwd_smem(int w, int s) {
+  return (((sizeof(PairTables) + 127) / 128 * 128 + sizeof(float4) * kSections * w + sizeof(uint64_t) * (kSections * w + s * w) + 127) / 128 * 128) +
+         sizeof(float) * kUnitFloats * s * w;
+}
+constexpr size_t bwd_smem(int w, int s) {
+  return (((sizeof(PairTables) + 127) / 128 * 128 + sizeof(float4) * kSections * w + sizeof(uint64_t) * (kSections * w + s * w) + 127) / 128 * 128) +
+         sizeof(float) * kUnitFloats * (2 * s + 4) * w;
+}
+template <int W, int S>
 int launch_fwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
-  constexpr size_t smem = Smem<W, kFwdStages, kFwdStages>::kBytes;
-  int rc = ensure_smem(eq_fwd_kernel<W>, smem);
+  constexpr size_t smem = Smem<W, S, S>::kBytes;
+  static_assert(smem == fwd_smem(W, S), "shared-memory formula out of sync");
+  int rc = ensure_smem(eq_fwd_kernel<W, S>, smem);
   if (rc != DASP_OK) return rc;
-  eq_fwd_kernel<W><<<(unsigned)pairs, W * 32, smem, st>>>(p);
+  eq_fwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("eq_fwd_kernel");
   return DASP_OK;
+}
+template <int S>
+int dispatch_fwd(int w, const EqParams& p, int64_t pairs, cudaStream_t st) {
+  switch (w) {
+    case 1: return launch_fwd_w<1, S>(p, pairs, st);
+    case 2: return launch_fwd_w<2, S>(p, pairs, st);
+    case 3: return launch_fwd_w<3, S>(p, pairs, st);
+    case 4: return launch_fwd_w<4, S>(p, pairs, st);
+    case 6: return launch_fwd_w<6, S>(p, pairs, st);
+    default: return launch_fwd_w<8, S>(p, pairs, st);
+  }
 }
 template <int W, int S>
 int launch_bwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
   constexpr size_t smem = Smem<W, BwdUnits<S>::kPerWarp, S>::kBytes;
+  static_assert(smem == bwd_smem(W, S), "shared-memory formula out of sync");
   static_assert(smem <= 227 * 1024, "backward variant does not fit in shared memory");
   int rc = ensure_smem(eq_bwd_kernel<W, S>, smem);
   if (rc != DASP_OK) return rc;
@@ -820,18 +861,14 @@ int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int6
   DASP_REQUIRE(sample_rate > 0.f, "eq fwd: sample_rate must be positive");
   const int64_t rows = bs * chs, pairs = (rows + 1) / 2;
   DASP_REQUIRE(pairs < (1ll << 31), "eq fwd: too many rows");
-  const int w = pick_warps(pairs, DASP_EQ_FWD_WARPS_PER_SM, 8, tune_fwd_w());
+  const int stages = tune_fwd_s() == 1 ? 1 : 2;
+  const int w = pick_warps(pairs, DASP_EQ_FWD_REGS, tune_fwd_w(), [&](int ww) { return fwd_smem(ww, stages); });
   EqParams p{};
   p.x = x; p.y = y; p.params = params; p.ckpt = ckpt; p.n = n; p.rows = rows; p.chs = (int)chs;
   p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;
   p.bulk = (n % 4 == 0) && aligned16(x) && aligned16(y);
   cudaStream_t st = (cudaStream_t)stream;
-  switch (w) {
-    case 1: return launch_fwd_w<1>(p, pairs, st);
-    case 2: return launch_fwd_w<2>(p, pairs, st);
-    case 4: return launch_fwd_w<4>(p, pairs, st);
-    default: return launch_fwd_w<8>(p, pairs, st);
-  }
+  return stages == 1 ? dispatch_fwd<1>(w, p, pairs, st) : dispatch_fwd<2>(w, p, pairs, st);
 }
 
 int dasp_eq_bwd(const float* gy, const float* x, const float* params, const float* ckpt, float* gx,
@@ -850,8 +887,10 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
     set_error("eq bwd: workspace needs %lld floats, got %lld", (long long)(rows * 30), (long long)ws_floats);
     return DASP_ERR_WORKSPACE;
   }
-  const int w = pick_warps(pairs, DASP_EQ_BWD_WARPS_PER_SM, 8, tune_bwd_w());
-  const int stages = (w == 8) ? 1 : (tune_bwd_s() == 1 ? 1 : 2);
+  int stages = tune_bwd_s() == 2 ? 2 : 1;
+  int w = pick_warps(pairs, 255, tune_bwd_w(), [&](int ww) { return bwd_smem(ww, stages); });
+  if (bwd_smem(w, stages) > kSmemPerSm) stages = 1;            // a pinned (W, S) pair that does not fit
+  if (bwd_smem(w, stages) > kSmemPerSm) w = 4;
   EqParams p{};
   p.x = x; p.gy = gy; p.y = gx; p.params = params; p.ckpt = const_cast<float*>(ckpt); p.partial = ws; p.n = n;
   p.rows = rows; p.chs = (int)chs; p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;
@@ -862,8 +901,11 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
     case 12: rc = launch_bwd_w<1, 2>(p, pairs, st); break;
     case 21: rc = launch_bwd_w<2, 1>(p, pairs, st); break;
     case 22: rc = launch_bwd_w<2, 2>(p, pairs, st); break;
+    case 31: rc = launch_bwd_w<3, 1>(p, pairs, st); break;
+    case 32: rc = launch_bwd_w<3, 2>(p, pairs, st); break;
     case 41: rc = launch_bwd_w<4, 1>(p, pairs, st); break;
     case 42: rc = launch_bwd_w<4, 2>(p, pairs, st); break;
+    case 61: rc = launch_bwd_w<6, 1>(p, pairs, st); break;
     default: rc = launch_bwd_w<8, 1>(p, pairs, st); break;
   }
   if (rc != DASP_OK) return rc;

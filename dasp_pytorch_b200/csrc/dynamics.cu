@@ -511,16 +511,29 @@ int pick_warps(int64_t bs, int chs, int nbuf_per_ch) {
   const int64_t want = 16ll * sm_count();
   int w = 1;
   while (w < 8 && bs * w < want) w *= 2;
-  if (debug_forced_warps()) w = debug_forced_warps();
+  { const int f = debug_forced_warps(); if (f == 1 || f == 2 || f == 4 || f == 8) w = f; }
   while (w > 1 && (size_t)kStages * nbuf_per_ch * chs * (w * 32 * kE) * 4 + kSmemHeader > 96 * 1024) w /= 2;
   return w;
+}
+// one-off opt-in to the largest dynamic shared memory any launch of `kernel` may ask for (pick_warps caps it at
+// 96 KB), cached per (host thread, device, kernel instantiation) instead of a driver call on every launch
+template <class K>
+int ensure_smem_optin(K kernel) {
+  static thread_local int done_dev = -1;
+  int dev = 0;
+  DASP_CUDA_OK(cudaGetDevice(&dev));
+  if (done_dev != dev) {
+    DASP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 256));
+    done_dev = dev;
+  }
+  return DASP_OK;
 }
 size_t smem_bytes(int w, int nbuf) { return kSmemHeader + (size_t)kStages * nbuf * (w * 32 * kE) * 4; }
 
 template <Curve CV, int W, bool LA>
 int launch_fwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
   const size_t smem = smem_bytes(W, p.chs);
-  DASP_CUDA_OK(cudaFuncSetAttribute(dynamics_fwd_kernel<CV, W, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { int rc = ensure_smem_optin(dynamics_fwd_kernel<CV, W, LA>); if (rc != DASP_OK) return rc; }
   dynamics_fwd_kernel<CV, W, LA><<<(unsigned)bs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("dynamics_fwd_kernel");
   return DASP_OK;
@@ -528,7 +541,7 @@ int launch_fwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
 template <Curve CV, int W, bool LA>
 int launch_bwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
   const size_t smem = smem_bytes(W, 2 * p.chs);
-  DASP_CUDA_OK(cudaFuncSetAttribute(dynamics_bwd_kernel<CV, W, LA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { int rc = ensure_smem_optin(dynamics_bwd_kernel<CV, W, LA>); if (rc != DASP_OK) return rc; }
   dynamics_bwd_kernel<CV, W, LA><<<(unsigned)bs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("dynamics_bwd_kernel");
   return DASP_OK;

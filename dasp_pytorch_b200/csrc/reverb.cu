@@ -685,6 +685,259 @@ ifft_mix_kernel(const float* __restrict__ Ypl, const float* __restrict__ twiddle
   }
 }
 
+// ---- the backward's block transforms on the same in-shared-memory FFT --------------------------------------
+// g_fft_kernel     = g_blocks_kernel + forward C2C:  Gs[i] = FFT([0 .. 0 | mix g block i]),  + dL/dmix partials
+// ifft_dx_kernel   = inverse C2C + finish_dx_blocks_kernel: one CTA walks the windows of an item in order and keeps
+//                    the second half of window i in registers until the first half of window i + 1 arrives, so the
+//                    overlap-add of the two windows that cover a sample needs no second pass and no atomics
+// ifft_irgrad_kernel = inverse C2C of the dL/dIR partitions + ir_grad_pp_kernel: the 4096 taps of a partition go to
+//                    shared memory and are correlated with the filtered noise f read class by class (coalesced)
+
+// Gb[(il*I + i)*kNbA + f] = FFT of [zeros(kB) | mix (g_left + i g_right)[i kB + m], m < kB];
+// mix_part[il*I + i] = sum over the block and both channels of g (wet - x)
+__global__ void __launch_bounds__(kFusedThreads, 1)
+g_fft_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ wet,
+             const float* __restrict__ params, float2* __restrict__ Gb, float* __restrict__ mix_part,
+             const float* __restrict__ twiddles, int64_t item0, int I, int64_t n, int in_chs, int nblocks) {
+  extern __shared__ __align__(128) float sm[];
+  FftSmem s(sm);
+  __shared__ float wp[kFusedThreads / 32];
+  const int t = threadIdx.x;
+  s.init(twiddles, t);
+  const fft8k::Tables tb = fft8k::carve_tables(s.tabf);
+  auto fetch = [&](int it, int m) {                // all threads: zero padding; thread 0: the bulk copies
+    if (m >= nblocks) return;
+    const int64_t il = m / I;
+    const int i = m - (int)il * I;
+    float* re = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    float* im = re + fft8k::kPlaneG;
+    const int64_t s0 = (int64_t)i * kB;            // first sample of the block (lands at offset kB of the window)
+    const int64_t rem = n - s0;
+    const int len = rem < kB ? (int)rem : kB;
+    for (int e = t; e < kB; e += kFusedThreads) { re[e] = 0.f; im[e] = 0.f; }
+    for (int e = kB + len + t; e < kNbA; e += kFusedThreads) { re[e] = 0.f; im[e] = 0.f; }
+    if (t == 0) {
+      const float* gl = gy + ((item0 + il) * 2) * n + s0;
+      uint64_t* bar = &s.full[it & 1];
+      mbar_arrive_expect_tx(bar, 2u * (uint32_t)len * 4u);
+      tma_load_1d(re + kB, gl, (uint32_t)len * 4u, bar);
+      tma_load_1d(im + kB, gl + n, (uint32_t)len * 4u, bar);
+    }
+  };
+  fetch(0, blockIdx.x);
+  fetch(1, blockIdx.x + gridDim.x);
+  __syncthreads();
+  int it = 0;
+  for (int m = blockIdx.x; m < nblocks; m += gridDim.x, ++it) {
+    mbar_wait(&s.full[it & 1], (uint32_t)((it >> 1) & 1));
+    float* gr = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    const int64_t il = m / I, b = item0 + il;
+    const int i = m - (int)il * I;
+    const float mix = params[b * 25 + 24];
+    // dL/dmix partial: the block's g sits in shared memory (second half of the planes), wet and x come from HBM
+    float acc = 0.f;
+    {
+      const float* xl = x + (b * in_chs) * n;
+      const float* xr = in_chs == 1 ? xl : xl + n;
+      const float* wl = wet + (b * 2) * n;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int mm = t + 512 * q;
+        const int64_t tg = (int64_t)i * kB + mm;
+        if (tg < n) {
+          const float g0 = gr[kB + mm], g1 = gr[fft8k::kPlaneG + kB + mm];
+          acc = fmaf(g0, wl[tg] - xl[tg], fmaf(g1, wl[n + tg] - xr[tg], acc));
+        }
+      }
+    }
+    __syncthreads();                                 // pass 1 transforms the planes in place
+    float xr_[16], xi_[16];
+    fft8192_in_smem<false>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2, m + 2 * gridDim.x); }, [] {}, xr_, xi_);
+    float2* out = Gb + (int64_t)m * kNbA;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) out[t + 512 * q] = make_float2(mix * xr_[q], mix * xi_[q]);
+    acc = warp_sum(acc);
+    if ((t & 31) == 0) wp[t >> 5] = acc;
+    __syncthreads();
+    if (t == 0) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < kFusedThreads / 32; ++w) sum += wp[w];
+      mix_part[m] = sum;
+    }
+    // (wp is next written after the barriers inside the following transform)
+  }
+}
+
+// gx[t] = (1-mix) g[t] + D[q][kB + t - q kB] + D[q+1][t - q kB], q = t / kB, from the planar product spectra Dpl
+// (one CTA per item at a time; mono input receives the sum of both channel gradients)
+__global__ void __launch_bounds__(kFusedThreads, 1)
+ifft_dx_kernel(const float* __restrict__ Dpl, const float* __restrict__ twiddles, const float* __restrict__ gy,
+               const float* __restrict__ params, float* __restrict__ gx, int64_t item0, int items, int I, int64_t n,
+               int in_chs) {
+  extern __shared__ __align__(128) float sm[];
+  FftSmem s(sm);
+  const int t = threadIdx.x;
+  s.init(twiddles, t);
+  const fft8k::Tables tb = fft8k::carve_tables(s.tabf);
+  // work list of this CTA: windows (il, i), il = blockIdx.x, blockIdx.x + gridDim.x, ..., i = 0 .. I-1
+  const int my_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_items * I;
+  auto fetch = [&](int it) {
+    if (t != 0 || it >= total) return;
+    const int64_t il = blockIdx.x + (int64_t)(it / I) * gridDim.x;
+    const int i = it % I;
+    uint64_t* bar = &s.full[it & 1];
+    float* dst = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    const float* src = Dpl + (il * I + i) * (int64_t)(2 * kNbA);
+    mbar_arrive_expect_tx(bar, 2u * kNbA * 4u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tma_load_1d(dst + q * 4096, src + q * 4096, 16384u, bar);
+  };
+  fetch(0);
+  fetch(1);
+  float pr[8], pi[8];                                // second half of the previous window of this item
+  for (int it = 0; it < total; ++it) {
+    mbar_wait(&s.full[it & 1], (uint32_t)((it >> 1) & 1));
+    float* gr = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    const int64_t il = blockIdx.x + (int64_t)(it / I) * gridDim.x, b = item0 + il;
+    const int i = it % I;
+    const float mix = params[b * 25 + 24];
+    const float* g0p = gy + (b * 2) * n;
+    // the block finished by this window is i - 1 (its first half); after the last window also block I - 1
+    float ga[8], gb[8];
+    float xr[16], xi[16];
+    fft8192_in_smem<true>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2); },
+                          [&] {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                              const int64_t t0 = (int64_t)(i - 1) * kB + (t + 512 * q);
+                              ga[q] = (i > 0 && t0 < n) ? g0p[t0] : 0.f;
+                              gb[q] = (i > 0 && t0 < n) ? g0p[n + t0] : 0.f;
+                            }
+                          },
+                          xr, xi);
+    const float om = 1.0f - mix;
+    if (i > 0) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int64_t tg = (int64_t)(i - 1) * kB + (t + 512 * q);
+        if (tg < n) {
+          const float o0 = fmaf(om, ga[q], pr[q] + xr[q]), o1 = fmaf(om, gb[q], pi[q] + xi[q]);
+          if (in_chs == 1) gx[b * n + tg] = o0 + o1;
+          else { gx[(b * 2) * n + tg] = o0; gx[(b * 2 + 1) * n + tg] = o1; }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { pr[q] = xr[q + 8]; pi[q] = xi[q + 8]; }
+    if (i == I - 1) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int64_t tg = (int64_t)i * kB + (t + 512 * q);
+        if (tg < n) {
+          const float o0 = fmaf(om, g0p[tg], pr[q]), o1 = fmaf(om, g0p[n + tg], pi[q]);
+          if (in_chs == 1) gx[b * n + tg] = o0 + o1;
+          else { gx[(b * 2) * n + tg] = o0; gx[(b * 2 + 1) * n + tg] = o1; }
+        }
+      }
+    }
+  }
+}
+
+// unit (il, j): dIR taps [j kB, (j+1) kB) = first half of IFFT(Epl[il][j]) (left, right);
+// part[((il*J + j)*12 + k)*2 + {0,1}] = sum_t (dIR_l f_l + dIR_r f_r) env_k(t) {1, tt(t)}  over the partition's taps,
+// f in the polyphase layout C[((il*12 + k)*R + c)*nb + a] = f[R a + c].
+__global__ void __launch_bounds__(kFusedThreads, 1)
+ifft_irgrad_kernel(const float* __restrict__ Epl, const float* __restrict__ twiddles, const float2* __restrict__ C,
+                   const float* __restrict__ params /* chunk x 25 */, float* __restrict__ part, int L, int leff, int J,
+                   int R, int nunits) {
+  constexpr int nb = fft8k::kN;
+  extern __shared__ __align__(128) float sm[];
+  FftSmem s(sm);
+  __shared__ float red[kFusedThreads / 32][2 * kBands];
+  __shared__ float rk[kBands];
+  __shared__ int cls_lo[17], cls_off[17];            // per class: first a of the partition, prefix count of taps
+  const int t = threadIdx.x;
+  s.init(twiddles, t);
+  const fft8k::Tables tb = fft8k::carve_tables(s.tabf);
+  auto fetch = [&](int it, int m) {
+    if (t != 0 || m >= nunits) return;
+    uint64_t* bar = &s.full[it & 1];
+    float* dst = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    const float* src = Epl + (int64_t)m * 2 * kNbA;
+    mbar_arrive_expect_tx(bar, 2u * kNbA * 4u);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) tma_load_1d(dst + q * 4096, src + q * 4096, 16384u, bar);
+  };
+  fetch(0, blockIdx.x);
+  fetch(1, blockIdx.x + gridDim.x);
+  const float step = 1.0f / (float)(L - 1);
+  float2* D = reinterpret_cast<float2*>(s.Yr);        // the partition's taps, after pass 4 has consumed Y
+  int it = 0;
+  for (int m = blockIdx.x; m < nunits; m += gridDim.x, ++it) {
+    mbar_wait(&s.full[it & 1], (uint32_t)((it >> 1) & 1));
+    float* gr = s.G + (it & 1) * 2 * fft8k::kPlaneG;
+    const int64_t il = m / J;
+    const int j = m - (int)il * J;
+    const int lo = j * kB, hi = (lo + kB < leff) ? lo + kB : leff;      // taps [lo, hi)
+    float xr[16], xi[16];
+    fft8192_in_smem<true>(gr, gr + fft8k::kPlaneG, s, tb, t, [&] { fetch(it + 2, m + 2 * gridDim.x); }, [] {}, xr, xi);
+    __syncthreads();                                  // every thread is done reading Y (pass 4) and the previous unit's D
+    if (t < kBands) rk[t] = -(params[il * 25 + kBands + t] * 10.0f + 1.0f);
+    if (t == 0) {
+      int off = 0;
+      for (int c = 0; c < R; ++c) {
+        const int a_lo = (lo - c + R - 1) / R, a_hi = (hi - c + R - 1) / R;      // taps R a + c in [lo, hi)
+        cls_lo[c] = a_lo;
+        cls_off[c] = off;
+        off += (a_hi > a_lo) ? a_hi - a_lo : 0;
+      }
+      cls_off[R] = off;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) D[t + 512 * q] = make_float2(xr[q], xi[q]);
+    __syncthreads();
+    float s0[kBands], s1[kBands];
+#pragma unroll
+    for (int k = 0; k < kBands; ++k) { s0[k] = 0.f; s1[k] = 0.f; }
+    const float2* cb = C + (il * kBands) * (int64_t)R * nb;
+    const int ntaps = cls_off[R];
+    for (int idx = t; idx < ntaps; idx += kFusedThreads) {
+      int c = 0;
+      while (c + 1 < R && idx >= cls_off[c + 1]) ++c;
+      const int a = cls_lo[c] + (idx - cls_off[c]);
+      const int tau = R * a + c;
+      const float2 gd = D[tau - lo];
+      const float tt = time_axis32(tau, L, step);
+      const float2* c0 = cb + (int64_t)c * nb + a;
+      float2 v[kBands];
+#pragma unroll
+      for (int k = 0; k < kBands; ++k) v[k] = c0[(int64_t)k * R * nb];
+#pragma unroll
+      for (int k = 0; k < kBands; ++k) {
+        const float w = fmaf(gd.x, v[k].x, gd.y * v[k].y) * __expf(rk[k] * tt);
+        s0[k] += w;
+        s1[k] = fmaf(w, tt, s1[k]);
+      }
+    }
+    const int lane = t & 31, warp = t >> 5;
+#pragma unroll
+    for (int k = 0; k < kBands; ++k) {
+      const float x0 = warp_sum(s0[k]), x1 = warp_sum(s1[k]);
+      if (lane == 0) { red[warp][2 * k] = x0; red[warp][2 * k + 1] = x1; }
+    }
+    __syncthreads();
+    if (t < 2 * kBands) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kFusedThreads / 32; ++w) acc += red[w][t];
+      part[((int64_t)m * kBands) * 2 + t] = acc;
+    }
+    // red / rk / cls_* / D are rewritten only after the __syncthreads that follows the next transform
+  }
+}
+
 // ---- fused IR synthesis (device-noise mode, nb == 8192, R <= 8) -------------------------------------
 // spectral_gen -> inverse FFT -> shape/accumulate as ONE kernel, so the 4.7 MB-per-item filtered-noise buffer is
 // written at most once (for the backward) instead of being written, transformed in place and read back.
@@ -1344,7 +1597,8 @@ void bwd_layout(const Geom& g, size_t cufft_work, BwdWs& w) {
   w.gs = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.ib * kNbA));
   w.ds = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.ib * kNbA));
   w.es = o; o += align256(sizeof(float2) * (size_t)(g.chunk * g.jb * kNbA));
-  const int64_t nparts = g.nbk > g.nparts_pp() ? g.nbk : g.nparts_pp();
+  int64_t nparts = g.nbk > g.nparts_pp() ? g.nbk : g.nparts_pp();
+  if (g.jb > nparts) nparts = g.jb;
   w.irpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * nparts * kBands * 2));
   w.mixpart = o; o += align256(sizeof(float) * (size_t)(g.chunk * g.ib));
   w.cufft = o; o += align256(cufft_work);
@@ -1371,6 +1625,9 @@ int configure_fft_kernels() {
     DASP_CUDA_OK(cudaFuncSetAttribute(ifft_shape_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
     DASP_CUDA_OK(cudaFuncSetAttribute(x_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
     DASP_CUDA_OK(cudaFuncSetAttribute(ifft_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
+    DASP_CUDA_OK(cudaFuncSetAttribute(g_fft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
+    DASP_CUDA_OK(cudaFuncSetAttribute(ifft_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
+    DASP_CUDA_OK(cudaFuncSetAttribute(ifft_irgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFftSmemBytes));
     configured[dev] = true;
   }
   return DASP_OK;
@@ -1615,33 +1872,69 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
     const float2* xs = (const float2*)xspec_save + item0 * I * (int64_t)kNbA;
     const float2* hs = (const float2*)irspec_save + item0 * J * (int64_t)kNbA;
 
-    g_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(gy, x, wet_save, params, ws_gs, ws_mixpart, item0, I,
-                                                                      n, (int)in_chs);
-    DASP_LAUNCH_OK("g_blocks_kernel");
-    DASP_CUFFT_OK(cufftSetStream(pl.xi_c2c.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.xi_c2c.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)ws_gs, (cufftComplex*)ws_gs, CUFFT_FORWARD));
-    launch_mac<true>(ws_gs, hs, ws_ds, I, J, I, items, inv, st);      // dx windows: sum_j conj(H[j]) G[q+j]
-    launch_mac<true>(ws_gs, xs, ws_es, I, I, J, items, inv, st);      // dIR partitions: sum_p conj(X[p]) G[j+p]
-    DASP_LAUNCH_OK("partition_mac_kernel<corr>");
-    DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)ws_ds, (cufftComplex*)ws_ds, CUFFT_INVERSE));
-    DASP_CUFFT_OK(cufftSetStream(pl.hj_c2c.h, st));
-    DASP_CUFFT_OK(cufftSetWorkArea(pl.hj_c2c.h, ws_cufft));
-    DASP_CUFFT_OK(cufftExecC2C(pl.hj_c2c.h, (cufftComplex*)ws_es, (cufftComplex*)ws_es, CUFFT_INVERSE));
-    finish_dx_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(gy, ws_ds, params, gx, item0, I, n,
-                                                                              (int)in_chs);
-    DASP_LAUNCH_OK("finish_dx_blocks_kernel");
-    int nparts;
-    if (polyphase) {
-      nparts = (int)g.nparts_pp();
-      ir_grad_pp_kernel<<<dim3((unsigned)nparts, (unsigned)items), 256, 0, st>>>(ws_es, C, params + item0 * 25, ws_irpart,
-                                                                                g.L, g.leff, J, (int)g.rpp, nb);
-    } else {
-      nparts = nbk;
-      ir_grad_pairs_kernel<<<dim3((unsigned)nbk, (unsigned)items), 256, 0, st>>>(ws_es, C, params + item0 * 25, ws_irpart,
-                                                                                  g.L, g.leff, J, nbk, nb, hop, P);
+    // block transforms on the own in-shared-memory FFT (fused with their neighbours) when the rows allow bulk copies;
+    // dasp_debug_reverb_path(1) pins the cuFFT pipeline (the two are compared by the tests)
+    const bool own_conv = debug_reverb_path() != 1 && (n % 4 == 0) && aligned16(gy);
+    const bool own_irgrad = own_conv && polyphase && nb == fft8k::kN && g.L < (int64_t)1 << 31;
+    const float* tw = nullptr;
+    if (own_conv) {
+      if ((rc = get_fft_tables(st, &tw)) != DASP_OK) return rc;
+      if ((rc = configure_fft_kernels()) != DASP_OK) return rc;
     }
-    DASP_LAUNCH_OK("ir_grad kernel");
+    const int nblk = (int)(items * I);
+    const unsigned fft_grid = (unsigned)(nblk < sm_count() ? nblk : sm_count());
+    if (own_conv) {
+      g_fft_kernel<<<fft_grid, kFusedThreads, kFftSmemBytes, st>>>(gy, x, wet_save, params, ws_gs, ws_mixpart, tw, item0, I, n,
+                                                                   (int)in_chs, nblk);
+      DASP_LAUNCH_OK("g_fft_kernel");
+      launch_mac<true, true>(ws_gs, hs, ws_ds, I, J, I, items, inv, st);      // dx windows: sum_j conj(H[j]) G[q+j]
+      DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+      const unsigned dx_grid = (unsigned)(items < sm_count() ? items : sm_count());
+      ifft_dx_kernel<<<dx_grid, kFusedThreads, kFftSmemBytes, st>>>(reinterpret_cast<const float*>(ws_ds), tw, gy, params, gx,
+                                                                    item0, (int)items, I, n, (int)in_chs);
+      DASP_LAUNCH_OK("ifft_dx_kernel");
+    } else {
+      g_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(gy, x, wet_save, params, ws_gs, ws_mixpart, item0,
+                                                                        I, n, (int)in_chs);
+      DASP_LAUNCH_OK("g_blocks_kernel");
+      DASP_CUFFT_OK(cufftSetStream(pl.xi_c2c.h, st));
+      DASP_CUFFT_OK(cufftSetWorkArea(pl.xi_c2c.h, ws_cufft));
+      DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)ws_gs, (cufftComplex*)ws_gs, CUFFT_FORWARD));
+      launch_mac<true>(ws_gs, hs, ws_ds, I, J, I, items, inv, st);
+      DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+      DASP_CUFFT_OK(cufftExecC2C(pl.xi_c2c.h, (cufftComplex*)ws_ds, (cufftComplex*)ws_ds, CUFFT_INVERSE));
+      finish_dx_blocks_kernel<<<dim3((unsigned)I, (unsigned)items), 256, 0, st>>>(gy, ws_ds, params, gx, item0, I, n,
+                                                                                (int)in_chs);
+      DASP_LAUNCH_OK("finish_dx_blocks_kernel");
+    }
+    int nparts;
+    if (own_irgrad) {
+      launch_mac<true, true>(ws_gs, xs, ws_es, I, I, J, items, inv, st);      // dIR partitions: sum_p conj(X[p]) G[j+p]
+      DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+      nparts = J;
+      const int nunits = (int)(items * J);
+      const unsigned ig_grid = (unsigned)(nunits < sm_count() ? nunits : sm_count());
+      ifft_irgrad_kernel<<<ig_grid, kFusedThreads, kFftSmemBytes, st>>>(reinterpret_cast<const float*>(ws_es), tw, C,
+                                                                        params + item0 * 25, ws_irpart, (int)g.L,
+                                                                        (int)g.leff, J, (int)g.rpp, nunits);
+      DASP_LAUNCH_OK("ifft_irgrad_kernel");
+    } else {
+      launch_mac<true>(ws_gs, xs, ws_es, I, I, J, items, inv, st);
+      DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+      DASP_CUFFT_OK(cufftSetStream(pl.hj_c2c.h, st));
+      DASP_CUFFT_OK(cufftSetWorkArea(pl.hj_c2c.h, ws_cufft));
+      DASP_CUFFT_OK(cufftExecC2C(pl.hj_c2c.h, (cufftComplex*)ws_es, (cufftComplex*)ws_es, CUFFT_INVERSE));
+      if (polyphase) {
+        nparts = (int)g.nparts_pp();
+        ir_grad_pp_kernel<<<dim3((unsigned)nparts, (unsigned)items), 256, 0, st>>>(ws_es, C, params + item0 * 25, ws_irpart,
+                                                                                  g.L, g.leff, J, (int)g.rpp, nb);
+      } else {
+        nparts = nbk;
+        ir_grad_pairs_kernel<<<dim3((unsigned)nbk, (unsigned)items), 256, 0, st>>>(ws_es, C, params + item0 * 25, ws_irpart,
+                                                                                    g.L, g.leff, J, nbk, nb, hop, P);
+      }
+      DASP_LAUNCH_OK("ir_grad kernel");
+    }
     reverb_param_grad_kernel<<<(unsigned)((items * 25 + 127) / 128), 128, 0, st>>>(ws_irpart, ws_mixpart, params, gparams,
                                                                                    item0, items, nparts, I);
     DASP_LAUNCH_OK("reverb_param_grad_kernel");

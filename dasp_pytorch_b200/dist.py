@@ -4,8 +4,8 @@ Every processor on the hot path is independent per batch item -- parameters are 
 side chain, the EQ's filter and the reverb's impulse response never mix items, and neither do the
 gradients -- so the path shards by contiguous batch chunks with NO collective inside it.  A collective is
 only needed at the edges, when one rank holds the whole batch: ``scatter_batch`` hands every rank its chunk
-(one ``torch.distributed.scatter``; NCCL over NVLink on the GPU box, gloo in the CPU tests) and
-``gather_batch`` collects the processed chunks back (one ``gather``).  One process per GPU; launch with
+(one grouped send/recv; NCCL over NVLink on the GPU box, gloo in the CPU tests) and
+``gather_batch`` collects the processed chunks back the same way.  One process per GPU; launch with
 ``torch.distributed.run``.
 """
 from __future__ import annotations
@@ -43,38 +43,61 @@ def shard_tensors(tensors: Sequence[torch.Tensor], world_size: int, rank: int, r
 
 def scatter_batch(full: Optional[torch.Tensor], batch: int, tail_shape: Sequence[int], dtype, device,
                   src: int = 0, group=None) -> torch.Tensor:
-    """rank ``src`` holds ``full`` of shape ``(batch, *tail_shape)``; every rank returns its chunk."""
+    """rank ``src`` holds ``full`` of shape ``(batch, *tail_shape)``; every rank returns its chunk.
+
+    One grouped send/recv (``batch_isend_irecv``: a single NCCL group launch on the GPU box): every receiver gets
+    exactly its rows straight out of ``full`` -- uneven shard sizes need no padding and the root makes no staging
+    copies (its own chunk is a view-copy on the device)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     sizes = shard_sizes(batch, world)
     mine = torch.empty((sizes[rank], *tail_shape), dtype=dtype, device=device)
-    pad = max(sizes)
-    buf = torch.zeros((pad, *tail_shape), dtype=dtype, device=device)     # scatter needs equal-size pieces
-    pieces = None
+    if world == 1:
+        mine.copy_(full)
+        return mine
+    ops = []
     if rank == src:
-        pieces = []
         off = 0
-        for s in sizes:
-            p = torch.zeros((pad, *tail_shape), dtype=dtype, device=device)
-            p[:s] = full[off: off + s]
-            pieces.append(p)
-            off += s
-    dist.scatter(buf, pieces, src=src, group=group)
-    mine.copy_(buf[: sizes[rank]])
+        for r, sz in enumerate(sizes):
+            piece = full[off: off + sz]
+            off += sz
+            if r == src:
+                mine.copy_(piece)
+            elif sz > 0:
+                ops.append(dist.P2POp(dist.isend, piece.contiguous(), r, group))
+    elif sizes[rank] > 0:
+        ops.append(dist.P2POp(dist.irecv, mine, src, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
     return mine
 
 
 def gather_batch(chunk: torch.Tensor, batch: int, dst: int = 0, group=None) -> Optional[torch.Tensor]:
-    """inverse of ``scatter_batch``: rank ``dst`` returns the ``(batch, ...)`` tensor, the others ``None``."""
+    """inverse of ``scatter_batch``: rank ``dst`` returns the ``(batch, ...)`` tensor, the others ``None``.
+    The receivers write straight into the rows of the result (no padding, no concatenation)."""
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     sizes = shard_sizes(batch, world)
-    pad = max(sizes)
-    buf = torch.zeros((pad, *chunk.shape[1:]), dtype=chunk.dtype, device=chunk.device)
-    buf[: sizes[rank]] = chunk
-    outs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, outs, dst=dst, group=group)
-    if rank != dst:
-        return None
-    return torch.cat([o[:s] for o, s in zip(outs, sizes)], dim=0)
+    if chunk.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank} holds {chunk.shape[0]} items, its shard of {batch} has {sizes[rank]}")
+    if world == 1:
+        return chunk.clone()
+    ops = []
+    out = None
+    if rank == dst:
+        out = torch.empty((batch, *chunk.shape[1:]), dtype=chunk.dtype, device=chunk.device)
+        off = 0
+        for r, sz in enumerate(sizes):
+            if r == dst:
+                out[off: off + sz].copy_(chunk)
+            elif sz > 0:
+                ops.append(dist.P2POp(dist.irecv, out[off: off + sz], r, group))
+            off += sz
+    elif sizes[rank] > 0:
+        ops.append(dist.P2POp(dist.isend, chunk.contiguous(), dst, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out
 
 
 def process_sharded(fn, x_full: Optional[torch.Tensor], params_full: Optional[Sequence[torch.Tensor]], batch: int,

@@ -16,6 +16,7 @@ done
 cat gpurun_out/a1_eq_variants.log
 timeout 1500 python -m pytest tests -m gpu -q --deselect tests/test_gpu_eq.py 2>&1 | tail -40 > gpurun_out/a1_all_tests.log
 tail -15 gpurun_out/a1_all_tests.log
+timeout 600 python tools/quick_bench.py --ops reverb,comp --bs 1024 2>&1 | grep -E "reverb|compressor" > gpurun_out/a1_reverb.log; cat gpurun_out/a1_reverb.log
 # ncu full-set capture of the EQ kernels (default variant choice) at 1024 x 2 x 48000
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:eq_ -s 2 -c 2 -o gpurun_out/a1_eq python tools/quick_bench.py --ops eq --bs 1024 > gpurun_out/a1_ncu.log 2>&1
 ls -la gpurun_out | tail -5
