@@ -61,9 +61,6 @@ constexpr int kE = DASP_EQ_E;    // samples per lane per tile (odd: conflict-fre
 static_assert(kE % 2 == 1, "E must be odd");
 constexpr int kTile = 32 * kE;   // samples per tile (one warp)
 constexpr int kSections = 6;
-#ifndef DASP_EQ_FWD_REGS
-#define DASP_EQ_FWD_REGS 90      // registers per thread of eq_fwd_kernel (ptxas -v), for the occupancy-aware choice of W
-#endif
 
 // ------------------------------------------------------------------ coefficient design (fp64)
 // forward-mode dual number with 3 directional derivatives (gain_dB, fc, Q)
@@ -763,35 +760,32 @@ int tune_bwd_s() {
   return debug_eq_bwd_stages() ? debug_eq_bwd_stages() : v;
 }
 
-// Warps per row pair.  All pairs should be resident at once (one wave: a second, partly filled wave costs more than a
-// few extra warps gain), so with c = ceil(pairs / SMs) CTAs per SM the largest W whose shared memory (and register
-// file share) still allows c CTAs per SM is taken; W in {1, 2, 3, 4, 6, 8}.
-constexpr int kWarpChoices[6] = {1, 2, 3, 4, 6, 8};
-constexpr size_t kSmemPerSm = 227 * 1024, kSmemCtaReserve = 1024;
-template <class SmemBytes>
-int pick_warps(int64_t pairs, int regs_per_thread, int tuned, SmemBytes smem_of) {
+// Warps per row pair (W in {1, 2, 3, 4, 6, 8}; 0 / other = automatic).  Measured on B200 at 1024 pairs x 48000
+// samples (profiles/r02_eq_variants.md): forward W=4 with two load stages (5 CTAs = 20 warps per SM) beats both W=2
+// (7 CTAs, 14 warps) and the single-wave choices W=3 / one stage; small batches want W=8 to fill the SMs at all.
+// The backward holds 255 registers per thread, i.e. 8 warps per SM whatever the split: W=8 with one stage (one CTA per
+// SM, least shared memory per warp) measured best.
+int pick_fwd_warps(int64_t pairs, int tuned) {
   const int f = debug_forced_warps() ? debug_forced_warps() : tuned;
-  for (int c : kWarpChoices) if (f == c) return f;
-  const int64_t sms = sm_count();
-  int64_t per_sm = (pairs + sms - 1) / sms;
-  if (per_sm < 1) per_sm = 1;
-  int best = 1;
-  for (int w : kWarpChoices) {
-    const bool fits_smem = (smem_of(w) + kSmemCtaReserve) * (size_t)per_sm <= kSmemPerSm;
-    const bool fits_regs = (int64_t)regs_per_thread * 32 * w * per_sm <= 65536;
-    if (fits_smem && fits_regs && w * per_sm <= 64) best = w;
-  }
-  return best;
+  if (f == 1 || f == 2 || f == 3 || f == 4 || f == 6 || f == 8) return f;
+  return (pairs * 4 < 20ll * sm_count()) ? 8 : 4;
 }
+int pick_bwd_warps(int tuned) {
+  const int f = debug_forced_warps() ? debug_forced_warps() : tuned;
+  if (f == 1 || f == 2 || f == 3 || f == 4 || f == 6 || f == 8) return f;
+  return 8;
+}
+constexpr size_t kSmemPerSm = 227 * 1024;
 
-// one-off opt-in to > 48 KB dynamic shared memory, cached per (device, kernel)
-template <class K>
-int ensure_smem(K kernel, size_t bytes) {
+// one-off opt-in to > 48 KB dynamic shared memory, cached per (host thread, device, kernel INSTANTIATION): the
+// kernel is a non-type template parameter, because every instantiation has the same function-pointer type
+template <auto Kernel>
+int ensure_smem(size_t bytes) {
   static thread_local int done_dev = -1;
   int dev = 0;
   DASP_CUDA_OK(cudaGetDevice(&dev));
   if (done_dev != dev) {
-    DASP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    DASP_CUDA_OK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     done_dev = dev;
   }
   return DASP_OK;
@@ -809,7 +803,7 @@ template <int W, int S>
 int launch_fwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
   constexpr size_t smem = Smem<W, S, S>::kBytes;
   static_assert(smem == fwd_smem(W, S), "shared-memory formula out of sync");
-  int rc = ensure_smem(eq_fwd_kernel<W, S>, smem);
+  int rc = ensure_smem<eq_fwd_kernel<W, S>>(smem);
   if (rc != DASP_OK) return rc;
   eq_fwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("eq_fwd_kernel");
@@ -831,7 +825,7 @@ int launch_bwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
   constexpr size_t smem = Smem<W, BwdUnits<S>::kPerWarp, S>::kBytes;
   static_assert(smem == bwd_smem(W, S), "shared-memory formula out of sync");
   static_assert(smem <= 227 * 1024, "backward variant does not fit in shared memory");
-  int rc = ensure_smem(eq_bwd_kernel<W, S>, smem);
+  int rc = ensure_smem<eq_bwd_kernel<W, S>>(smem);
   if (rc != DASP_OK) return rc;
   eq_bwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("eq_bwd_kernel");
@@ -862,7 +856,7 @@ int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int6
   const int64_t rows = bs * chs, pairs = (rows + 1) / 2;
   DASP_REQUIRE(pairs < (1ll << 31), "eq fwd: too many rows");
   const int stages = tune_fwd_s() == 1 ? 1 : 2;
-  const int w = pick_warps(pairs, DASP_EQ_FWD_REGS, tune_fwd_w(), [&](int ww) { return fwd_smem(ww, stages); });
+  const int w = pick_fwd_warps(pairs, tune_fwd_w());
   EqParams p{};
   p.x = x; p.y = y; p.params = params; p.ckpt = ckpt; p.n = n; p.rows = rows; p.chs = (int)chs;
   p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;
@@ -888,9 +882,8 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
     return DASP_ERR_WORKSPACE;
   }
   int stages = tune_bwd_s() == 2 ? 2 : 1;
-  int w = pick_warps(pairs, 255, tune_bwd_w(), [&](int ww) { return bwd_smem(ww, stages); });
+  const int w = pick_bwd_warps(tune_bwd_w());
   if (bwd_smem(w, stages) > kSmemPerSm) stages = 1;            // a pinned (W, S) pair that does not fit
-  if (bwd_smem(w, stages) > kSmemPerSm) w = 4;
   EqParams p{};
   p.x = x; p.gy = gy; p.y = gx; p.params = params; p.ckpt = const_cast<float*>(ckpt); p.partial = ws; p.n = n;
   p.rows = rows; p.chs = (int)chs; p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;

@@ -516,14 +516,14 @@ int pick_warps(int64_t bs, int chs, int nbuf_per_ch) {
   return w;
 }
 // one-off opt-in to the largest dynamic shared memory any launch of `kernel` may ask for (pick_warps caps it at
-// 96 KB), cached per (host thread, device, kernel instantiation) instead of a driver call on every launch
-template <class K>
-int ensure_smem_optin(K kernel) {
+// 96 KB), cached per (host thread, device, kernel instantiation: a non-type template parameter) instead of a driver call on every launch
+template <auto Kernel>
+int ensure_smem_optin() {
   static thread_local int done_dev = -1;
   int dev = 0;
   DASP_CUDA_OK(cudaGetDevice(&dev));
   if (done_dev != dev) {
-    DASP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 256));
+    DASP_CUDA_OK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 256));
     done_dev = dev;
   }
   return DASP_OK;
@@ -533,7 +533,7 @@ size_t smem_bytes(int w, int nbuf) { return kSmemHeader + (size_t)kStages * nbuf
 template <Curve CV, int W, bool LA>
 int launch_fwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
   const size_t smem = smem_bytes(W, p.chs);
-  { int rc = ensure_smem_optin(dynamics_fwd_kernel<CV, W, LA>); if (rc != DASP_OK) return rc; }
+  { int rc = ensure_smem_optin<dynamics_fwd_kernel<CV, W, LA>>(); if (rc != DASP_OK) return rc; }
   dynamics_fwd_kernel<CV, W, LA><<<(unsigned)bs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("dynamics_fwd_kernel");
   return DASP_OK;
@@ -541,7 +541,7 @@ int launch_fwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
 template <Curve CV, int W, bool LA>
 int launch_bwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
   const size_t smem = smem_bytes(W, 2 * p.chs);
-  { int rc = ensure_smem_optin(dynamics_bwd_kernel<CV, W, LA>); if (rc != DASP_OK) return rc; }
+  { int rc = ensure_smem_optin<dynamics_bwd_kernel<CV, W, LA>>(); if (rc != DASP_OK) return rc; }
   dynamics_bwd_kernel<CV, W, LA><<<(unsigned)bs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("dynamics_bwd_kernel");
   return DASP_OK;
