@@ -207,10 +207,15 @@ def reference_chain_seconds(mod, bs, device, rev_kw=None, reps=1, seed=1):
 
 
 def cpu_arm(budget_s, warm=True):
-    """the reference's CPU path on all host cores: bs = 4, 8, 16 as far as the time budget
-    allows; returns (samples/s at the largest batch finished, detail dict)"""
+    """the reference's CPU path on the host cores: bs = 4, 8, 16 as far as the time budget
+    allows; returns (samples/s at the largest batch finished, detail dict).
+
+    Thread count: torchrun exports OMP_NUM_THREADS=1 and a 128-core box is NOT fastest with 128 intra-op threads (the
+    reference's grouped conv1d collapses there: 372 s for 4 items in round 2's first run, against ~25 s with 32
+    threads), so a one-item pass is timed at 32 threads and at all cores and the faster setting is kept -- the reference
+    gets the best configuration found, and `cores` reports it."""
     import torch
-    torch.set_num_threads(os.cpu_count() or 1)            # torchrun exports OMP_NUM_THREADS=1: undo it
+    ncpu = os.cpu_count() or 1
     ref = load_reference()
     if ref is not None:
         mod, kind, kw = ref, "reference", {}
@@ -218,25 +223,33 @@ def cpu_arm(budget_s, warm=True):
         import oracle
         mod, kind, kw = oracle, "port", {"method": "direct"}
     t_start = time.perf_counter()
-    if warm:
-        reference_chain_seconds(mod, 1, "cpu", kw)         # one untimed pass (thread pools, allocator, scipy firwin)
-    rates, times = {}, {}
+    cal = {}
+    for t in sorted({min(32, ncpu), ncpu}):
+        torch.set_num_threads(t)
+        cal[t] = reference_chain_seconds(mod, 1, "cpu", kw)   # doubles as the warm-up pass (thread pools, scipy firwin)
+        if cal[t] > 0.25 * budget_s:
+            break
+    best_t = min(cal, key=lambda k: cal[k])
+    torch.set_num_threads(best_t)
+    rates, times = {1: CHS * N_SAMPLES / cal[best_t]}, {1: cal[best_t]}
     for bs in (4, 8, 16):
-        if rates and (time.perf_counter() - t_start) + 2.2 * times[max(times)] > budget_s:
+        est = times[max(times)] * bs / max(times)              # linear extrapolation from the largest batch done
+        if (time.perf_counter() - t_start) + 1.1 * est > budget_s:
             break
         sec = reference_chain_seconds(mod, bs, "cpu", kw)
         times[bs] = sec
         rates[bs] = bs * CHS * N_SAMPLES / sec
     top = max(rates)
     lin = max(rates.values()) / min(rates.values())
-    detail = {"kind": kind, "cores": torch.get_num_threads(), "host_cpus": os.cpu_count(),
+    detail = {"kind": kind, "cores": best_t, "host_cpus": ncpu,
+              "threads_tried_s_per_item": {str(k): round(v, 2) for k, v in cal.items()},
               "rates_by_batch": {str(k): round(v, 1) for k, v in rates.items()},
               "seconds_by_batch": {str(k): round(v, 2) for k, v in times.items()},
               "linearity_max_over_min": round(lin, 3),
-              "sample": f"{top} items x 2ch x 48000 (of the {GLOBAL_BATCH}-item batch), full chain fwd+bwd, "
+              "sample": f"{top} item(s) x 2ch x 48000 (of the {GLOBAL_BATCH}-item batch), full chain fwd+bwd, "
                         f"{'the unmodified reference (baseline/_ref)' if kind == 'reference' else 'oracle port of the reference algorithm'}"
-                        ": FFT-grid IIRs, time-domain conv1d reverb, CPU noise; all host threads; per-sample rate "
-                        "extrapolates linearly to the full batch"}
+                        f": FFT-grid IIRs, time-domain conv1d reverb, CPU noise; {best_t} intra-op threads (best of those "
+                        "tried); per-sample rate extrapolates linearly to the full batch"}
     return rates[top], times[top], top, detail
 
 
@@ -247,10 +260,10 @@ def run_reference_arm(args, rank, world):
     val, sec, bs, detail = cpu_arm(budget_s=170.0, warm=args.warmup > 0)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": len(detail["rates_by_batch"]), "steps_requested": args.steps, "warmup": 1 if args.warmup > 0 else 0,
-        "warmup_requested": args.warmup,
-        "note": "a CPU step takes tens of seconds: the run is capped at ~3 minutes whatever --steps says; the timed "
-                "steps are one fwd+bwd each at batch 4, 8, 16 (as many as fit), value = rate at the largest",
+        "steps": len(detail["rates_by_batch"]), "steps_requested": args.steps, "warmup": 0, "warmup_requested": args.warmup,
+        "note": "a CPU step takes tens of seconds: the run is capped at ~3 minutes whatever --steps / --warmup say; the "
+                "timed steps are one fwd+bwd each at batch 1 (thread-count calibration, doubles as warm-up), 4, 8, 16 "
+                "(as many as fit), value = rate at the largest batch finished",
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": make_config(args.batch, max(world, 1), args.scaling, None, graph=False),
         "cpu_baseline": {"value": val, "unit": UNIT, **detail},

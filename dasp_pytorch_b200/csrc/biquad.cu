@@ -61,6 +61,7 @@ constexpr int kE = DASP_EQ_E;    // samples per lane per tile (odd: conflict-fre
 static_assert(kE % 2 == 1, "E must be odd");
 constexpr int kTile = 32 * kE;   // samples per tile (one warp)
 constexpr int kSections = 6;
+constexpr size_t kSmemPerSm = 227 * 1024;     // usable shared memory of one SM / one CTA
 
 // ------------------------------------------------------------------ coefficient design (fp64)
 // forward-mode dual number with 3 directional derivatives (gain_dB, fc, Q)
@@ -144,10 +145,26 @@ __device__ inline M2d mpow(double sg, double q, unsigned n) {
 }
 
 // ------------------------------------------------------------------ packed fp32x2 helpers (x = row A, y = row B)
+// DASP_EQ_PACKED = 1 issues Blackwell's packed FFMA2/FMUL2/FADD2; 0 (default) issues two scalar instructions per pair.
+// Measured on B200 (tools/probe/ffma2_probe2.cu, profiles/r02_ffma2_probe.md): an FFMA2 whose three operands are three
+// DISTINCT register pairs (the situation of every recurrence step here) occupies the FMA pipe for ~4.3 cycles per
+// warp, two scalar FFMAs for ~2.4 -- the packed form halves the issue slots but nearly halves the FMA throughput,
+// and the first round-2 version of these kernels ran AT that FFMA2 pipe limit (89 %).  The row-pair organisation is
+// kept (tables, shuffles' control flow and address arithmetic are shared by the two rows); only the arithmetic is
+// issued as scalar FFMA.
+#ifndef DASP_EQ_PACKED
+#define DASP_EQ_PACKED 0
+#endif
 typedef float2 f2;
+#if DASP_EQ_PACKED
 __device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ f2 fmul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ f2 fadd2(f2 a, f2 b) { return __fadd2_rn(a, b); }
+#else
+__device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ f2 fmul2(f2 a, f2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ f2 fadd2(f2 a, f2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+#endif
 __device__ __forceinline__ f2 zero2() { return make_float2(0.f, 0.f); }
 __device__ __forceinline__ f2 shfl_up2(f2 v, int d) {
   return make_float2(__shfl_up_sync(0xffffffffu, v.x, d), __shfl_up_sync(0xffffffffu, v.y, d));
@@ -775,7 +792,6 @@ int pick_bwd_warps(int tuned) {
   if (f == 1 || f == 2 || f == 3 || f == 4 || f == 6 || f == 8) return f;
   return 8;
 }
-constexpr size_t kSmemPerSm = 227 * 1024;
 
 // one-off opt-in to > 48 KB dynamic shared memory, cached per (host thread, device, kernel INSTANTIATION): the
 // kernel is a non-type template parameter, because every instantiation has the same function-pointer type
@@ -803,11 +819,16 @@ template <int W, int S>
 int launch_fwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
   constexpr size_t smem = Smem<W, S, S>::kBytes;
   static_assert(smem == fwd_smem(W, S), "shared-memory formula out of sync");
-  int rc = ensure_smem<eq_fwd_kernel<W, S>>(smem);
-  if (rc != DASP_OK) return rc;
-  eq_fwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
-  DASP_LAUNCH_OK("eq_fwd_kernel");
-  return DASP_OK;
+  if constexpr (smem <= kSmemPerSm) {
+    int rc = ensure_smem<eq_fwd_kernel<W, S>>(smem);
+    if (rc != DASP_OK) return rc;
+    eq_fwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
+    DASP_LAUNCH_OK("eq_fwd_kernel");
+    return DASP_OK;
+  } else {
+    set_error("eq fwd: variant W=%d S=%d needs %zu bytes of shared memory", W, S, smem);
+    return DASP_ERR_INVALID;
+  }
 }
 template <int S>
 int dispatch_fwd(int w, const EqParams& p, int64_t pairs, cudaStream_t st) {
@@ -824,12 +845,16 @@ template <int W, int S>
 int launch_bwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
   constexpr size_t smem = Smem<W, BwdUnits<S>::kPerWarp, S>::kBytes;
   static_assert(smem == bwd_smem(W, S), "shared-memory formula out of sync");
-  static_assert(smem <= 227 * 1024, "backward variant does not fit in shared memory");
-  int rc = ensure_smem<eq_bwd_kernel<W, S>>(smem);
-  if (rc != DASP_OK) return rc;
-  eq_bwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
-  DASP_LAUNCH_OK("eq_bwd_kernel");
-  return DASP_OK;
+  if constexpr (smem <= kSmemPerSm) {
+    int rc = ensure_smem<eq_bwd_kernel<W, S>>(smem);
+    if (rc != DASP_OK) return rc;
+    eq_bwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
+    DASP_LAUNCH_OK("eq_bwd_kernel");
+    return DASP_OK;
+  } else {
+    set_error("eq bwd: variant W=%d S=%d needs %zu bytes of shared memory", W, S, smem);
+    return DASP_ERR_INVALID;
+  }
 }
 
 }  // namespace
@@ -855,8 +880,10 @@ int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int6
   DASP_REQUIRE(sample_rate > 0.f, "eq fwd: sample_rate must be positive");
   const int64_t rows = bs * chs, pairs = (rows + 1) / 2;
   DASP_REQUIRE(pairs < (1ll << 31), "eq fwd: too many rows");
-  const int stages = tune_fwd_s() == 1 ? 1 : 2;
-  const int w = pick_fwd_warps(pairs, tune_fwd_w());
+  int stages = tune_fwd_s() == 1 ? 1 : 2;
+  int w = pick_fwd_warps(pairs, tune_fwd_w());
+  if (fwd_smem(w, stages) > kSmemPerSm) stages = 1;
+  while (w > 1 && fwd_smem(w, stages) > kSmemPerSm) w = (w == 8) ? 6 : (w == 6) ? 4 : (w == 4) ? 3 : w - 1;
   EqParams p{};
   p.x = x; p.y = y; p.params = params; p.ckpt = ckpt; p.n = n; p.rows = rows; p.chs = (int)chs;
   p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;
@@ -882,8 +909,9 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
     return DASP_ERR_WORKSPACE;
   }
   int stages = tune_bwd_s() == 2 ? 2 : 1;
-  const int w = pick_bwd_warps(tune_bwd_w());
-  if (bwd_smem(w, stages) > kSmemPerSm) stages = 1;            // a pinned (W, S) pair that does not fit
+  int w = pick_bwd_warps(tune_bwd_w());
+  if (bwd_smem(w, stages) > kSmemPerSm) stages = 1;            // a (W, S) pair that does not fit: fewer stages, then
+  while (w > 1 && bwd_smem(w, stages) > kSmemPerSm) w = (w == 8) ? 6 : (w == 6) ? 4 : (w == 4) ? 3 : w - 1;   // fewer warps
   EqParams p{};
   p.x = x; p.gy = gy; p.y = gx; p.params = params; p.ckpt = const_cast<float*>(ckpt); p.partial = ws; p.n = n;
   p.rows = rows; p.chs = (int)chs; p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;

@@ -43,7 +43,14 @@ constexpr int kPlaneY = 9216;          // floats per plane of the padded buffer 
 constexpr int kTabFloats = 2 * (2 * 64) + 2 * (2 * 512) + 2 * 1024 + 2 * 128;   // see Tables
 
 // ---- packed lane pair ------------------------------------------------------------------------------
-#if defined(__CUDA_ARCH__)
+// DASP_FFT_PACKED = 1: the lane pair is one packed fp32x2 register pair (FADD2/FMUL2/FFMA2); 0 (default): the same
+// two lanes as two scalar instructions.  See biquad.cu / profiles/r02_ffma2_probe.md: packed instructions with
+// distinct register-pair operands occupy the FMA pipe almost twice as long as the two scalar ones they replace, and
+// the round-1 FFT kernels sat at that limit (FMA pipe "22 %" by instruction count = ~95 % by pipe cycles).
+#ifndef DASP_FFT_PACKED
+#define DASP_FFT_PACKED 0
+#endif
+#if defined(__CUDA_ARCH__) && DASP_FFT_PACKED
 struct V2 { float2 v; };
 DASP_HD V2 v2(float a, float b) { V2 r; r.v = make_float2(a, b); return r; }
 DASP_HD V2 bc(float a) { return v2(a, a); }
@@ -57,6 +64,20 @@ DASP_HD float lane0(V2 a) { return a.v.x; }
 DASP_HD float lane1(V2 a) { return a.v.y; }
 DASP_HD V2 ld2(const float* p) { V2 r; r.v = *reinterpret_cast<const float2*>(p); return r; }
 DASP_HD void st2(float* p, V2 a) { *reinterpret_cast<float2*>(p) = a.v; }
+#elif defined(__CUDA_ARCH__)
+struct V2 { float x, y; };
+DASP_HD V2 v2(float a, float b) { V2 r; r.x = a; r.y = b; return r; }
+DASP_HD V2 bc(float a) { return v2(a, a); }
+DASP_HD V2 operator+(V2 a, V2 b) { return v2(a.x + b.x, a.y + b.y); }
+DASP_HD V2 operator-(V2 a, V2 b) { return v2(a.x - b.x, a.y - b.y); }
+DASP_HD V2 operator*(V2 a, V2 b) { return v2(a.x * b.x, a.y * b.y); }
+DASP_HD V2 fma2(V2 a, V2 b, V2 c) { return v2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+DASP_HD V2 fnma2(V2 a, V2 b, V2 c) { return v2(fmaf(-a.x, b.x, c.x), fmaf(-a.y, b.y, c.y)); }
+DASP_HD V2 neg(V2 a) { return v2(-a.x, -a.y); }
+DASP_HD float lane0(V2 a) { return a.x; }
+DASP_HD float lane1(V2 a) { return a.y; }
+DASP_HD V2 ld2(const float* p) { const float2 t = *reinterpret_cast<const float2*>(p); return v2(t.x, t.y); }
+DASP_HD void st2(float* p, V2 a) { *reinterpret_cast<float2*>(p) = make_float2(a.x, a.y); }
 #else
 struct V2 { float x, y; };
 DASP_HD V2 v2(float a, float b) { V2 r; r.x = a; r.y = b; return r; }

@@ -225,6 +225,15 @@ __global__ void cmul_filter_pairs_kernel(float2* __restrict__ C, const float2* _
   }
 }
 
+// packed fp32x2 helpers of the generator's R-point DFT: scalar pairs unless DASP_FFT_PACKED (see fft8192.cuh)
+#if DASP_FFT_PACKED
+__device__ __forceinline__ float2 gen_ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 gen_fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+#else
+__device__ __forceinline__ float2 gen_ffma2(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 gen_fmul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+#endif
+
 // ---- spectral synthesis (device-noise mode) ------------------------------------------------------
 // The band-filtered noise only has to be a stationary Gaussian process with the FIR's autocovariance on
 // the window [0, leff).  A length-n1 PERIODIC white sequence filtered circularly has exactly that
@@ -330,14 +339,14 @@ __device__ __forceinline__ void spectral_unit(int j1, int nb, const float2* __re
 #pragma unroll
     for (int j2 = 0; j2 < R; ++j2) {
       const int m = (j2 * b) % R;
-      sre = __ffma2_rn(gx[j2], rx[m], __ffma2_rn(gy[j2], nry[m], sre));
-      sim = __ffma2_rn(gx[j2], ry[m], __ffma2_rn(gy[j2], rx[m], sim));
+      sre = gen_ffma2(gx[j2], rx[m], gen_ffma2(gy[j2], nry[m], sre));
+      sim = gen_ffma2(gx[j2], ry[m], gen_ffma2(gy[j2], rx[m], sim));
     }
-    const float2 ore = __ffma2_rn(sre, tx, __fmul2_rn(sim, make_float2(-ty.x, -ty.y)));
-    const float2 oim = __ffma2_rn(sre, ty, __fmul2_rn(sim, tx));
+    const float2 ore = gen_ffma2(sre, tx, gen_fmul2(sim, make_float2(-ty.x, -ty.y)));
+    const float2 oim = gen_ffma2(sre, ty, gen_fmul2(sim, tx));
     emit(b, make_float2(ore.x, oim.x), make_float2(ore.y, oim.y));
-    const float2 ntx = __ffma2_rn(tx, wx, __fmul2_rn(ty, nwy));
-    ty = __ffma2_rn(tx, wy, __fmul2_rn(ty, wx));
+    const float2 ntx = gen_ffma2(tx, wx, gen_fmul2(ty, nwy));
+    ty = gen_ffma2(tx, wy, gen_fmul2(ty, wx));
     tx = ntx;
   }
 }
