@@ -144,26 +144,22 @@ __device__ inline M2d mpow(double sg, double q, unsigned n) {
   return r;
 }
 
-// ------------------------------------------------------------------ packed fp32x2 helpers (x = row A, y = row B)
-// DASP_EQ_PACKED = 1 issues Blackwell's packed FFMA2/FMUL2/FADD2; 0 (default) issues two scalar instructions per pair.
-// Measured on B200 (tools/probe/ffma2_probe2.cu, profiles/r02_ffma2_probe.md): an FFMA2 whose three operands are three
-// DISTINCT register pairs (the situation of every recurrence step here) occupies the FMA pipe for ~4.3 cycles per
-// warp, two scalar FFMAs for ~2.4 -- the packed form halves the issue slots but nearly halves the FMA throughput,
-// and the first round-2 version of these kernels ran AT that FFMA2 pipe limit (89 %).  The row-pair organisation is
-// kept (tables, shuffles' control flow and address arithmetic are shared by the two rows); only the arithmetic is
-// issued as scalar FFMA.
+// ------------------------------------------------------------------ arithmetic on row pairs (x = row A, y = row B)
+// DASP_EQ_PACKED = 1 (default) issues Blackwell's packed FFMA2/FMUL2/FADD2 where both operands are row pairs; 0 issues
+// two scalar instructions per pair.  Measured on B200 (profiles/r02_ffma2_probe.md, profiles/r02_eq_variants.md): in a
+// micro-benchmark an FFMA2 with three distinct register-pair operands occupies the FMA pipe ~4.3 cycles per warp
+// (two scalar FFMAs: ~2.4), but inside these kernels the packed form still wins (forward 0.39 vs 0.45 ms): operand
+// reuse between neighbouring instructions is high and the halved issue count matters more.
 #ifndef DASP_EQ_PACKED
-#define DASP_EQ_PACKED 0
+#define DASP_EQ_PACKED 1
 #endif
 typedef float2 f2;
 #if DASP_EQ_PACKED
 __device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ f2 fmul2(f2 a, f2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ f2 fadd2(f2 a, f2 b) { return __fadd2_rn(a, b); }
 #else
 __device__ __forceinline__ f2 ffma2(f2 a, f2 b, f2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
 __device__ __forceinline__ f2 fmul2(f2 a, f2 b) { return make_float2(a.x * b.x, a.y * b.y); }
-__device__ __forceinline__ f2 fadd2(f2 a, f2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 #endif
 __device__ __forceinline__ f2 zero2() { return make_float2(0.f, 0.f); }
 __device__ __forceinline__ f2 shfl_up2(f2 v, int d) {
@@ -175,33 +171,47 @@ __device__ __forceinline__ f2 shfl_down2(f2 v, int d) {
 __device__ __forceinline__ f2 shfl2(f2 v, int l) {
   return make_float2(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l));
 }
+
+// Coefficient type C of the per-pair tables:
+//   float : both rows of the pair belong to the SAME item (every pair when the channel count is even -- stereo), so
+//           one scalar coefficient serves both rows: half the table bytes, a whole 2x2 matrix per 128-bit load, and
+//           the coefficient register is shared by the two scalar FMAs of the pair.  The first packed version of these
+//           kernels ran with the shared-memory / shuffle pipe 68 % busy (ncu: l1tex__data_pipe_lsu_wavefronts, 762
+//           wavefronts per tile, most of them broadcast 128-bit table loads); this halves that traffic.
+//   f2    : the rows belong to different items (odd channel counts): (row A, row B) coefficient pairs, packed FFMA2.
+__device__ __forceinline__ f2 cfma(float c, f2 v, f2 a) { return make_float2(fmaf(c, v.x, a.x), fmaf(c, v.y, a.y)); }
+__device__ __forceinline__ f2 cfma(f2 c, f2 v, f2 a) { return ffma2(c, v, a); }
+__device__ __forceinline__ f2 dup(float c) { return make_float2(c, c); }
+__device__ __forceinline__ f2 dup(f2 c) { return c; }
+
 struct St { f2 s1, s2; };                     // the 2-state vector of both rows
-struct M4 { f2 a, b, c, d; };                 // 2x2 matrix per row: [[a,b],[c,d]]
-__device__ __forceinline__ M4 ldm(const f2* p) {
+template <class C> struct M4 { C a, b, c, d; };   // 2x2 matrix [[a,b],[c,d]]
+__device__ __forceinline__ M4<float> ldm(const float* p) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  return {t.x, t.y, t.z, t.w};
+}
+__device__ __forceinline__ M4<f2> ldm(const f2* p) {
   const float4 lo = *reinterpret_cast<const float4*>(p), hi = *reinterpret_cast<const float4*>(p + 2);
   return {make_float2(lo.x, lo.y), make_float2(lo.z, lo.w), make_float2(hi.x, hi.y), make_float2(hi.z, hi.w)};
 }
-__device__ __forceinline__ St mv(const M4& m, const St& v) {          // M v
-  return {ffma2(m.a, v.s1, fmul2(m.b, v.s2)), ffma2(m.c, v.s1, fmul2(m.d, v.s2))};
+template <class C>
+__device__ __forceinline__ St mv_acc(const M4<C>& m, const St& v, const St& acc) {     // acc + M v
+  return {cfma(m.a, v.s1, cfma(m.b, v.s2, acc.s1)), cfma(m.c, v.s1, cfma(m.d, v.s2, acc.s2))};
 }
-__device__ __forceinline__ St mtv(const M4& m, const St& v) {         // M^T v
-  return {ffma2(m.a, v.s1, fmul2(m.c, v.s2)), ffma2(m.b, v.s1, fmul2(m.d, v.s2))};
-}
-__device__ __forceinline__ St mv_acc(const M4& m, const St& v, const St& acc) {     // acc + M v
-  return {ffma2(m.a, v.s1, ffma2(m.b, v.s2, acc.s1)), ffma2(m.c, v.s1, ffma2(m.d, v.s2, acc.s2))};
-}
-__device__ __forceinline__ St mtv_acc(const M4& m, const St& v, const St& acc) {    // acc + M^T v
-  return {ffma2(m.a, v.s1, ffma2(m.c, v.s2, acc.s1)), ffma2(m.b, v.s1, ffma2(m.d, v.s2, acc.s2))};
+template <class C>
+__device__ __forceinline__ St mtv_acc(const M4<C>& m, const St& v, const St& acc) {    // acc + M^T v
+  return {cfma(m.a, v.s1, cfma(m.c, v.s2, acc.s1)), cfma(m.b, v.s1, cfma(m.d, v.s2, acc.s2))};
 }
 
 // ------------------------------------------------------------------ shared-memory tables of one row pair
 constexpr int kStepSlots = 6;     // A^(E 2^s), s = 0..4, and the zero matrix (lanes a scan step does not touch)
-struct __align__(16) PairTables {
-  f2 cf[kSections][6];                    // sg, q, be1, B2, b0, pad
-  float4 fix[kSections][kE];              // first row of A^j: (a_j rowA, a_j rowB, b_j rowA, b_j rowB)
-  f2 step[kSections][kStepSlots][4];      // (a, b, c, d) pairs
-  f2 lane[kSections][32][4];              // A^(E l)
-  f2 warp[kSections][4];                  // A^(32 E)
+template <class C>
+struct __align__(16) Tables {
+  C cf[kSections][8];                     // sg, q, be1, B2, b0, pad x3
+  C fix[kSections][kE][2];                // first row of A^j: (a_j, b_j)
+  C step[kSections][kStepSlots][4];       // (a, b, c, d)
+  C lane[kSections][32][4];               // A^(E l)
+  C warp[kSections][4];                   // A^(32 E)
 };
 constexpr int kPowPerSection = kE + 5 + 32 + 1;
 
@@ -220,24 +230,28 @@ struct EqParams {
   int bulk;
 };
 
-// build the tables of the pair (row A of item ia, row B of item ib): every thread of the CTA participates;
-// ends with __syncthreads()
-__device__ void build_tables(PairTables& tb, const float* params, int64_t ia, int64_t ib, float sample_rate) {
+// component h of coefficient slot `dst` (a scalar table has one component, a pair table two)
+__device__ __forceinline__ void put_coef(float& dst, int, float v) { dst = v; }
+__device__ __forceinline__ void put_coef(f2& dst, int h, float v) { if (h == 0) dst.x = v; else dst.y = v; }
+template <class C> struct Halves { static constexpr int n = 1; };
+template <> struct Halves<f2> { static constexpr int n = 2; };
+
+// build the tables of the pair (row A of item ia, row B of item ib; ia == ib for C = float): every thread of the CTA
+// participates; ends with __syncthreads()
+template <class C>
+__device__ void build_tables(Tables<C>& tb, const float* params, int64_t ia, int64_t ib, float sample_rate) {
   __shared__ double cfd[2][kSections][2];   // sg, q in fp64 for the matrix powers
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const int halves = (ia == ib) ? 1 : 2;
+  constexpr int halves = Halves<C>::n;
   for (int e = tid; e < halves * kSections; e += nthr) {
     const int h = e / kSections, k = e - h * kSections;
     const float* p18 = params + (h == 0 ? ia : ib) * 18;
     const SigmaCoef sc = design_section((double)p18[3 * k], (double)p18[3 * k + 1], (double)p18[3 * k + 2],
                                         (double)sample_rate, section_kind(k));
-    float* cf = reinterpret_cast<float*>(&tb.cf[k][0]);
 #pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      const float v = (float)sc.c[j].v;
-      if (halves == 1) { cf[2 * j] = v; cf[2 * j + 1] = v; } else { cf[2 * j + h] = v; }
-    }
-    if (halves == 1 || h == 0) { cf[10] = 0.f; cf[11] = 0.f; }
+    for (int j = 0; j < 5; ++j) put_coef(tb.cf[k][j], h, (float)sc.c[j].v);
+#pragma unroll
+    for (int j = 5; j < 8; ++j) put_coef(tb.cf[k][j], h, 0.f);
     cfd[h][k][0] = sc.c[0].v;
     cfd[h][k][1] = sc.c[1].v;
   }
@@ -254,26 +268,42 @@ __device__ void build_tables(PairTables& tb, const float* params, int64_t ia, in
     const M2d m = mpow(cfd[h][k][0], cfd[h][k][1], n);
     const float ma = (float)m.a, mb = (float)m.b, mc = (float)m.c, md = (float)m.d;
     if (e < kE) {
-      float* f = reinterpret_cast<float*>(&tb.fix[k][e]);
-      if (halves == 1) { f[0] = ma; f[1] = ma; f[2] = mb; f[3] = mb; } else { f[h] = ma; f[2 + h] = mb; }
+      put_coef(tb.fix[k][e][0], h, ma);
+      put_coef(tb.fix[k][e][1], h, mb);
     } else {
-      float* f;
-      if (e < kE + 5) f = reinterpret_cast<float*>(&tb.step[k][e - kE][0]);
-      else if (e < kE + 5 + 32) f = reinterpret_cast<float*>(&tb.lane[k][e - kE - 5][0]);
-      else f = reinterpret_cast<float*>(&tb.warp[k][0]);
-      if (halves == 1) { f[0] = ma; f[1] = ma; f[2] = mb; f[3] = mb; f[4] = mc; f[5] = mc; f[6] = md; f[7] = md; }
-      else { f[h] = ma; f[2 + h] = mb; f[4 + h] = mc; f[6 + h] = md; }
+      C* f;
+      if (e < kE + 5) f = &tb.step[k][e - kE][0];
+      else if (e < kE + 5 + 32) f = &tb.lane[k][e - kE - 5][0];
+      else f = &tb.warp[k][0];
+      put_coef(f[0], h, ma); put_coef(f[1], h, mb); put_coef(f[2], h, mc); put_coef(f[3], h, md);
     }
   }
-  for (int e = tid; e < kSections * 8; e += nthr) reinterpret_cast<float*>(&tb.step[e / 8][5][0])[e % 8] = 0.f;
+  for (int e = tid; e < halves * kSections * 4; e += nthr) {
+    const int h = e / (kSections * 4), r = e - h * (kSections * 4);
+    put_coef(tb.step[r / 4][5][r % 4], h, 0.f);
+  }
   __syncthreads();
 }
 
+// the five section coefficients, expanded to row pairs for the (packed) local passes
 struct Cf { f2 sg, q, be1, B2, b0; };
-__device__ __forceinline__ Cf load_cf(const PairTables& tb, int k) {
+__device__ __forceinline__ Cf load_cf(const Tables<float>& tb, int k) {
+  const float4 a = *reinterpret_cast<const float4*>(&tb.cf[k][0]);
+  return {dup(a.x), dup(a.y), dup(a.z), dup(a.w), dup(tb.cf[k][4])};
+}
+__device__ __forceinline__ Cf load_cf(const Tables<f2>& tb, int k) {
   const float4 a = *reinterpret_cast<const float4*>(&tb.cf[k][0]);
   const float4 b = *reinterpret_cast<const float4*>(&tb.cf[k][2]);
   return {make_float2(a.x, a.y), make_float2(a.z, a.w), make_float2(b.x, b.y), make_float2(b.z, b.w), tb.cf[k][4]};
+}
+// fix-up table entry j of section k: (a_j, b_j)
+__device__ __forceinline__ void load_fix(const Tables<float>& tb, int k, int j, float& a, float& b) {
+  const float2 t = *reinterpret_cast<const float2*>(&tb.fix[k][j][0]);
+  a = t.x; b = t.y;
+}
+__device__ __forceinline__ void load_fix(const Tables<f2>& tb, int k, int j, f2& a, f2& b) {
+  const float4 t = *reinterpret_cast<const float4*>(&tb.fix[k][j][0]);
+  a = make_float2(t.x, t.y); b = make_float2(t.z, t.w);
 }
 
 // zero-state local pass of section k over the lane's E samples (in place); returns the end state.
@@ -291,10 +321,20 @@ __device__ __forceinline__ St local_pass(f2 (&v)[kE], const Cf& c) {
   }
   return {s1, s2};
 }
+// y[j] += (A^j s_in)_1
+template <class C>
+__device__ __forceinline__ void fix_up(f2 (&v)[kE], const Tables<C>& tb, int k, const St& sin) {
+#pragma unroll
+  for (int j = 0; j < kE; ++j) {
+    C a, b;
+    load_fix(tb, k, j, a, b);
+    v[j] = cfma(a, sin.s1, cfma(b, sin.s2, v[j]));
+  }
+}
 
 // ------------------------------------------------------------------ warp scans of the lanes' 2-vectors
-// per-lane byte offsets of the step matrices: the real power where the Kogge-Stone step applies to this lane, the
-// zero matrix otherwise (so the step is 2 LDS.128 + 4 SHFL + 4 FFMA2 without predicates or selects)
+// per-lane slot of the step matrices: the real power where the Kogge-Stone step applies to this lane, the zero matrix
+// otherwise (so a step is matrix loads + 4 SHFL + 4 FMAs per row without predicates or selects)
 struct StepOffsets { int o[5]; };
 __device__ __forceinline__ StepOffsets fwd_offsets(int lane) {
   StepOffsets s;
@@ -309,10 +349,10 @@ __device__ __forceinline__ StepOffsets rev_offsets(int lane) {
   return s;
 }
 
-// forward in time.  v: end state of the lane's zero-state local pass.  Returns the inclusive scan; `excl` = the
-// contribution of the lower lanes to the state entering this lane's chunk, `tot` = lane 31's inclusive value.
-__device__ __forceinline__ void scan_fwd(St v, const PairTables& tb, int k, const StepOffsets& so, int lane, St& excl,
-                                         St& tot) {
+// forward in time.  v: end state of the lane's zero-state local pass.  On return v is the inclusive scan (lane 31
+// holds the tile total) and `excl` the contribution of the lower lanes to the state entering this lane's chunk.
+template <class C>
+__device__ __forceinline__ void scan_fwd(St& v, const Tables<C>& tb, int k, const StepOffsets& so, int lane, St& excl) {
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     const St u = {shfl_up2(v.s1, 1 << s), shfl_up2(v.s2, 1 << s)};
@@ -320,11 +360,11 @@ __device__ __forceinline__ void scan_fwd(St v, const PairTables& tb, int k, cons
   }
   excl = {shfl_up2(v.s1, 1), shfl_up2(v.s2, 1)};
   if (lane == 0) excl = {zero2(), zero2()};
-  tot = {shfl2(v.s1, 31), shfl2(v.s2, 31)};
 }
-// reverse in time (adjoint): v = adjoint state at the lane's first sample after a zero-terminal local reverse pass
-__device__ __forceinline__ void scan_rev(St v, const PairTables& tb, int k, const StepOffsets& so, int lane, St& excl,
-                                         St& tot) {
+// reverse in time (adjoint): v = adjoint state at the lane's first sample after a zero-terminal local reverse pass;
+// on return lane 0 holds the tile total
+template <class C>
+__device__ __forceinline__ void scan_rev(St& v, const Tables<C>& tb, int k, const StepOffsets& so, int lane, St& excl) {
 #pragma unroll
   for (int s = 0; s < 5; ++s) {
     const St u = {shfl_down2(v.s1, 1 << s), shfl_down2(v.s2, 1 << s)};
@@ -332,12 +372,12 @@ __device__ __forceinline__ void scan_rev(St v, const PairTables& tb, int k, cons
   }
   excl = {shfl_down2(v.s1, 1), shfl_down2(v.s2, 1)};
   if (lane == 31) excl = {zero2(), zero2()};
-  tot = {shfl2(v.s1, 0), shfl2(v.s2, 0)};
 }
 
 // ------------------------------------------------------------------ carry mailboxes between the warps of a CTA
 // mailbox (k, w): carry of section k entering the next tile of warp w; written by the warp of the preceding tile.
 // Use number u of a mailbox completes phase u of its mbarrier (tile/sequence 0 is pre-arrived with a zero carry).
+// With W == 1 the same mailboxes carry the state from one tile to the next of the single warp (__syncwarp only).
 template <int W>
 struct Mail {
   float4* data;     // [kSections][W]
@@ -347,20 +387,19 @@ struct Mail {
     fence_barrier_init();
     for (int k = 0; k < kSections; ++k) {
       data[k * W + 0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      mbar_arrive(&bar[k * W + 0]);
+      if (W > 1) mbar_arrive(&bar[k * W + 0]);
     }
   }
   __device__ __forceinline__ St take(int k, int w, int use) {
-    mbar_wait(&bar[k * W + w], (uint32_t)(use & 1));
+    if (W > 1) mbar_wait(&bar[k * W + w], (uint32_t)(use & 1));
     const float4 d = data[k * W + w];
-    __syncwarp();                                    // every lane has its copy before lane 0 may trigger a refill
+    __syncwarp();                                    // every lane has its copy before the refill may be triggered
     return {make_float2(d.x, d.y), make_float2(d.z, d.w)};
   }
-  __device__ __forceinline__ void put(int k, int w, const St& c, int lane) {
-    if (lane == 0) {
-      data[k * W + w] = make_float4(c.s1.x, c.s1.y, c.s2.x, c.s2.y);
-      mbar_arrive(&bar[k * W + w]);
-    }
+  // called by ONE lane (the one that holds the tile total)
+  __device__ __forceinline__ void put(int k, int w, const St& c) {
+    data[k * W + w] = make_float4(c.s1.x, c.s1.y, c.s2.x, c.s2.y);
+    if (W > 1) mbar_arrive(&bar[k * W + w]);
   }
 };
 
@@ -411,16 +450,16 @@ __device__ __forceinline__ void warp_store(const float* unit, float* a, float* b
 }
 
 // dynamic shared memory carve-up
-template <int W, int UNITS_PER_WARP, int BARS_PER_WARP>
+template <class C, int W, int UNITS_PER_WARP, int BARS_PER_WARP>
 struct Smem {
-  PairTables* tb; float4* mail_data; uint64_t* mail_bar; uint64_t* full; float* units;
-  static constexpr size_t kTab = (sizeof(PairTables) + 127) / 128 * 128;
+  Tables<C>* tb; float4* mail_data; uint64_t* mail_bar; uint64_t* full; float* units;
+  static constexpr size_t kTab = (sizeof(Tables<C>) + 127) / 128 * 128;
   static constexpr size_t kMailData = sizeof(float4) * kSections * W;
   static constexpr size_t kBars = sizeof(uint64_t) * (kSections * W + BARS_PER_WARP * W);
   static constexpr size_t kHdr = (kTab + kMailData + kBars + 127) / 128 * 128;
   static constexpr size_t kBytes = kHdr + sizeof(float) * kUnitFloats * UNITS_PER_WARP * W;
   __device__ __forceinline__ explicit Smem(unsigned char* base) {
-    tb = reinterpret_cast<PairTables*>(base);
+    tb = reinterpret_cast<Tables<C>*>(base);
     mail_data = reinterpret_cast<float4*>(base + kTab);
     mail_bar = reinterpret_cast<uint64_t*>(base + kTab + kMailData);
     full = mail_bar + kSections * W;
@@ -428,40 +467,45 @@ struct Smem {
   }
 };
 
-// =============================================================================== forward
-template <int W, int S>
-__global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
-  constexpr int kFwdStages = S;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  using SM = Smem<W, kFwdStages, kFwdStages>;
-  SM sm(smem_raw);
-  const PairTables& tb = *sm.tb;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row_a = 2 * (int64_t)blockIdx.x;
-  const bool has_b = row_a + 1 < p.rows;
-  const int64_t row_b = has_b ? row_a + 1 : row_a;
+// the two rows of pair `pair`: pairs never straddle items when C = float (pairs per item = ceil(chs / 2), the last
+// pair of an item with an odd channel count would repeat its row -- but odd channel counts use C = f2, where pairs
+// are simply consecutive rows)
+struct PairRows { int64_t row_a, row_b; bool has_b; };
+__device__ __forceinline__ PairRows pair_rows(int64_t pair, int64_t rows) {
+  PairRows r;
+  r.row_a = 2 * pair;
+  r.has_b = r.row_a + 1 < rows;
+  r.row_b = r.has_b ? r.row_a + 1 : r.row_a;
+  return r;
+}
 
-  build_tables(*sm.tb, p.params, row_a / p.chs, row_b / p.chs, p.sample_rate);
+// =============================================================================== forward
+template <class C, int W, int S>
+__global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using SM = Smem<C, W, S, S>;
+  SM sm(smem_raw);
+  const Tables<C>& tb = *sm.tb;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const PairRows pr = pair_rows(blockIdx.x, p.rows);
+
+  build_tables(*sm.tb, p.params, pr.row_a / p.chs, pr.row_b / p.chs, p.sample_rate);
   Mail<W> mail{sm.mail_data, sm.mail_bar};
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kFwdStages * W; ++i) mbar_init(&sm.full[i], 1);
-    if (W > 1) mail.init_all(); else fence_barrier_init();
+    for (int i = 0; i < S * W; ++i) mbar_init(&sm.full[i], 1);
+    mail.init_all();
   }
   __syncthreads();
 
-  const RowPair rp{p.n, p.ntiles, p.bulk != 0, has_b};
-  const float* xa = p.x + row_a * p.n;
-  const float* xb = p.x + row_b * p.n;
-  float* ya = p.y + row_a * p.n;
-  float* yb = p.y + row_b * p.n;
-  float* my_units = sm.units + (size_t)warp * kFwdStages * kUnitFloats;
-  uint64_t* my_full = sm.full + warp * kFwdStages;
+  const RowPair rp{p.n, p.ntiles, p.bulk != 0, pr.has_b};
+  const float* xa = p.x + pr.row_a * p.n;
+  const float* xb = p.x + pr.row_b * p.n;
+  float* ya = p.y + pr.row_a * p.n;
+  float* yb = p.y + pr.row_b * p.n;
+  float* my_units = sm.units + (size_t)warp * S * kUnitFloats;
+  uint64_t* my_full = sm.full + warp * S;
   const StepOffsets so = fwd_offsets(lane);
   float4* ckpt = p.ckpt ? reinterpret_cast<float4*>(p.ckpt) + (int64_t)blockIdx.x * p.ntiles * kSections : nullptr;
-
-  St carry[kSections];                      // W == 1: the tile-to-tile carries live in registers
-#pragma unroll
-  for (int k = 0; k < kSections; ++k) carry[k] = {zero2(), zero2()};
 
   if (S > 1 && warp < p.ntiles) warp_load(my_units, xa, xb, warp, rp, &my_full[0], lane);
   int jt = 0;
@@ -495,22 +539,15 @@ __global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
 #pragma unroll
     for (int k = 0; k < kSections; ++k) {
       const Cf c = load_cf(tb, k);
-      const St end = local_pass(v, c);
-      St excl, tot;
-      scan_fwd(end, tb, k, so, lane, excl, tot);
-      St cin;                                                     // carry of section k entering this tile
-      if (W > 1) cin = mail.take(k, warp, jt); else cin = carry[k];
-      if (i + 1 < p.ntiles) {
-        const St cnext = mv_acc(ldm(&tb.warp[k][0]), cin, tot);   // A^(32E) c + total
-        if (W > 1) mail.put(k, (warp + 1) % W, cnext, lane); else carry[k] = cnext;
-      }
+      St incl = local_pass(v, c);
+      St excl;
+      scan_fwd(incl, tb, k, so, lane, excl);
+      const St cin = mail.take(k, warp, jt);                      // carry of section k entering this tile
+      if (lane == 31 && i + 1 < p.ntiles)                         // lane 31 holds the tile total
+        mail.put(k, (warp + 1) % W, mv_acc(ldm(&tb.warp[k][0]), cin, incl));      // A^(32E) c + total
       if (ckpt && lane == 0) ckpt[(int64_t)i * kSections + k] = make_float4(cin.s1.x, cin.s1.y, cin.s2.x, cin.s2.y);
       const St sin = mv_acc(ldm(&tb.lane[k][lane][0]), cin, excl);    // state entering this lane's chunk
-#pragma unroll
-      for (int j = 0; j < kE; ++j) {
-        const float4 t = tb.fix[k][j];                            // y[j] += (A^j s_in)_1
-        v[j] = ffma2(make_float2(t.x, t.y), sin.s1, ffma2(make_float2(t.z, t.w), sin.s2, v[j]));
-      }
+      fix_up(v, tb, k, sin);
     }
 #pragma unroll
     for (int j = 0; j < kE; ++j) { unit[off + j] = v[j].x; unit[kTile + off + j] = v[j].y; }
@@ -525,23 +562,23 @@ __global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
 template <int S>
 struct BwdUnits { static constexpr int kPerWarp = 2 * S + 4; };
 
-template <int W, int S>
+template <class C, int W, int S>
 __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  using SM = Smem<W, BwdUnits<S>::kPerWarp, S>;
+  using SM = Smem<C, W, BwdUnits<S>::kPerWarp, S>;
   SM sm(smem_raw);
-  const PairTables& tb = *sm.tb;
+  const Tables<C>& tb = *sm.tb;
   __shared__ double red[W][kSections * 5][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t row_a = 2 * (int64_t)blockIdx.x;
-  const bool has_b = row_a + 1 < p.rows;
-  const int64_t row_b = has_b ? row_a + 1 : row_a;
+  const PairRows pr = pair_rows(blockIdx.x, p.rows);
+  const int64_t row_a = pr.row_a, row_b = pr.row_b;
+  const bool has_b = pr.has_b;
 
   build_tables(*sm.tb, p.params, row_a / p.chs, row_b / p.chs, p.sample_rate);
   Mail<W> mail{sm.mail_data, sm.mail_bar};
   if (threadIdx.x == 0) {
     for (int i = 0; i < S * W; ++i) mbar_init(&sm.full[i], 1);
-    if (W > 1) mail.init_all(); else fence_barrier_init();
+    mail.init_all();
   }
   __syncthreads();
 
@@ -560,11 +597,9 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
   const StepOffsets so_f = fwd_offsets(lane), so_r = rev_offsets(lane);
   const float4* ckpt = reinterpret_cast<const float4*>(p.ckpt) + (int64_t)blockIdx.x * p.ntiles * kSections;
 
-  St adj[kSections];                               // W == 1: adjoint carries in registers
   f2 acc[kSections][5];
 #pragma unroll
   for (int k = 0; k < kSections; ++k) {
-    adj[k] = {zero2(), zero2()};
 #pragma unroll
     for (int q = 0; q < 5; ++q) acc[k][q] = zero2();
   }
@@ -613,37 +648,45 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
     f2* U5 = reinterpret_cast<f2*>(gu);            // input of section 5, interleaved, over the consumed dL/dy unit
     const int off = lane * kE;
     const int64_t n0 = (int64_t)tile * kTile + off;
+    const bool full_tile = (int64_t)(tile + 1) * kTile <= p.n;       // warp-uniform
 
     f2 gq[kE];                                     // dL/dy of the lane's samples; becomes dL/du_k section by section
+    if (full_tile) {
 #pragma unroll
-    for (int j = 0; j < kE; ++j)
-      gq[j] = (n0 + j < p.n) ? make_float2(gu[off + j], gu[kTile + off + j]) : zero2();
+      for (int j = 0; j < kE; ++j) gq[j] = make_float2(gu[off + j], gu[kTile + off + j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < kE; ++j)
+        gq[j] = (n0 + j < p.n) ? make_float2(gu[off + j], gu[kTile + off + j]) : zero2();
+    }
     __syncwarp();                                  // all lanes hold their dL/dy before the unit is overwritten
 
     // ---- phase F: recompute the section inputs u_1..u_5 and every section's state entering the lane's chunk ----
     St sin[kSections];
     {
       f2 v[kE];
+      if (full_tile) {
 #pragma unroll
-      for (int j = 0; j < kE; ++j)
-        v[j] = (n0 + j < p.n) ? make_float2(xu[off + j], xu[kTile + off + j]) : zero2();
+        for (int j = 0; j < kE; ++j) v[j] = make_float2(xu[off + j], xu[kTile + off + j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kE; ++j)
+          v[j] = (n0 + j < p.n) ? make_float2(xu[off + j], xu[kTile + off + j]) : zero2();
+      }
 #pragma unroll
       for (int k = 0; k < kSections; ++k) {
         const Cf c = load_cf(tb, k);
-        const St end = local_pass(v, c);
-        St excl, tot;
-        scan_fwd(end, tb, k, so_f, lane, excl, tot);
+        St incl = local_pass(v, c);
+        St excl;
+        scan_fwd(incl, tb, k, so_f, lane, excl);
         const float4 ck = ckpt[(int64_t)tile * kSections + k];
         const St cin = {make_float2(ck.x, ck.y), make_float2(ck.z, ck.w)};
         sin[k] = mv_acc(ldm(&tb.lane[k][lane][0]), cin, excl);
         if (k < kSections - 1) {
+          fix_up(v, tb, k, sin[k]);
           f2* uk = (k == kSections - 2) ? U5 + off : U + (size_t)k * kTile + off;
 #pragma unroll
-          for (int j = 0; j < kE; ++j) {
-            const float4 t = tb.fix[k][j];
-            v[j] = ffma2(make_float2(t.x, t.y), sin[k].s1, ffma2(make_float2(t.z, t.w), sin[k].s2, v[j]));
-            uk[j] = v[j];
-          }
+          for (int j = 0; j < kE; ++j) uk[j] = v[j];
         }
       }
     }
@@ -654,9 +697,14 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
       const Cf c = load_cf(tb, k);
       f2 u[kE], s1[kE], s2[kE];
       if (k == 0) {
+        if (full_tile) {
 #pragma unroll
-        for (int j = 0; j < kE; ++j)
-          u[j] = (n0 + j < p.n) ? make_float2(xu[off + j], xu[kTile + off + j]) : zero2();
+          for (int j = 0; j < kE; ++j) u[j] = make_float2(xu[off + j], xu[kTile + off + j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kE; ++j)
+            u[j] = (n0 + j < p.n) ? make_float2(xu[off + j], xu[kTile + off + j]) : zero2();
+        }
       } else {
         const f2* uk = (k == kSections - 1) ? U5 + off : U + (size_t)(k - 1) * kTile + off;
 #pragma unroll
@@ -673,7 +721,7 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
           a2 = ffma2(c.sg, a2, tb2);
         }
       }
-      St agg_v;
+      St incl;
       {  // zero-terminal reverse pass: only the value reaching the chunk's first sample is needed
         f2 l1 = zero2(), l2 = zero2();
 #pragma unroll
@@ -682,16 +730,13 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
           l2 = ffma2(c.sg, l2, l1);
           l1 = t1;
         }
-        agg_v = {l1, l2};
+        incl = {l1, l2};
       }
-      St excl, tot;
-      scan_rev(agg_v, tb, k, so_r, lane, excl, tot);
-      St ain;                                      // adjoint state at the first sample of the NEXT tile (in time)
-      if (W > 1) ain = mail.take(k, warp, jt); else ain = adj[k];
-      if (seq + 1 < p.ntiles) {
-        const St anext = mtv_acc(ldm(&tb.warp[k][0]), ain, tot);
-        if (W > 1) mail.put(k, (warp + 1) % W, anext, lane); else adj[k] = anext;
-      }
+      St excl;
+      scan_rev(incl, tb, k, so_r, lane, excl);
+      const St ain = mail.take(k, warp, jt);       // adjoint state at the first sample of the NEXT tile (in time)
+      if (lane == 0 && seq + 1 < p.ntiles)         // lane 0 holds the tile total of the reverse scan
+        mail.put(k, (warp + 1) % W, mtv_acc(ldm(&tb.warp[k][0]), ain, incl));
       // distance from the first sample of lane+1's chunk to the first sample of the next tile: (31-lane) chunks
       const St din = mtv_acc(ldm(&tb.lane[k][31 - lane][0]), ain, excl);
       {  // final reverse pass with the true terminal adjoint state
@@ -763,8 +808,8 @@ __global__ void eq_param_grad_kernel(const float* __restrict__ partial, const fl
 }
 
 // ---- host side -----------------------------------------------------------------------------
-// experiment knobs (read once): DASP_EQ_FWD_W / DASP_EQ_BWD_W = warps per row pair, DASP_EQ_BWD_S = stages of the
-// backward's x / dL/dy units.  0 / unset = automatic.
+// experiment knobs (read once): DASP_EQ_FWD_W / DASP_EQ_BWD_W = warps per row pair, DASP_EQ_FWD_S / DASP_EQ_BWD_S =
+// load stages per warp.  0 / unset = automatic.
 int env_int(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
@@ -776,20 +821,22 @@ int tune_bwd_s() {
   static const int v = env_int("DASP_EQ_BWD_S");
   return debug_eq_bwd_stages() ? debug_eq_bwd_stages() : v;
 }
+// force the general (pair-coefficient) tables even when every pair lies inside one item: test hook via the env
+int tune_force_pair_tables() { static const int v = env_int("DASP_EQ_PAIR_TABLES"); return v; }
 
-// Warps per row pair (W in {1, 2, 3, 4, 6, 8}; 0 / other = automatic).  Measured on B200 at 1024 pairs x 48000
-// samples (profiles/r02_eq_variants.md): forward W=4 with two load stages (5 CTAs = 20 warps per SM) beats both W=2
-// (7 CTAs, 14 warps) and the single-wave choices W=3 / one stage; small batches want W=8 to fill the SMs at all.
-// The backward holds 255 registers per thread, i.e. 8 warps per SM whatever the split: W=8 with one stage (one CTA per
-// SM, least shared memory per warp) measured best.
+// Warps per row pair (W in {1, 2, 4, 8}; 0 / other = automatic).  Measured on B200 at 1024 pairs x 48000 samples
+// (profiles/r02_eq_variants.md): forward W=4 with two load stages beats W=2 and the single-wave choices; small batches
+// want W=8 to fill the SMs at all.  The backward holds 255 registers per thread, i.e. 8 warps per SM whatever the
+// split: W=8 with one stage (one CTA per SM, least shared memory per warp) measured best.
+bool valid_w(int w) { return w == 1 || w == 2 || w == 4 || w == 8; }
 int pick_fwd_warps(int64_t pairs, int tuned) {
   const int f = debug_forced_warps() ? debug_forced_warps() : tuned;
-  if (f == 1 || f == 2 || f == 3 || f == 4 || f == 6 || f == 8) return f;
+  if (valid_w(f)) return f;
   return (pairs * 4 < 20ll * sm_count()) ? 8 : 4;
 }
 int pick_bwd_warps(int tuned) {
   const int f = debug_forced_warps() ? debug_forced_warps() : tuned;
-  if (f == 1 || f == 2 || f == 3 || f == 4 || f == 6 || f == 8) return f;
+  if (valid_w(f)) return f;
   return 8;
 }
 
@@ -807,22 +854,13 @@ int ensure_smem(size_t bytes) {
   return DASP_OK;
 }
 
-constexpr size_t fwd_smem(int w, int s) {
-  return (((sizeof(PairTables) + 127) / 128 * 128 + sizeof(float4) * kSections * w + sizeof(uint64_t) * (kSections * w + s * w) + 127) / 128 * 128) +
-         sizeof(float) * kUnitFloats * s * w;
-}
-constexpr size_t bwd_smem(int w, int s) {
-  return (((sizeof(PairTables) + 127) / 128 * 128 + sizeof(float4) * kSections * w + sizeof(uint64_t) * (kSections * w + s * w) + 127) / 128 * 128) +
-         sizeof(float) * kUnitFloats * (2 * s + 4) * w;
-}
-template <int W, int S>
-int launch_fwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
-  constexpr size_t smem = Smem<W, S, S>::kBytes;
-  static_assert(smem == fwd_smem(W, S), "shared-memory formula out of sync");
+template <class C, int W, int S>
+int launch_fwd(const EqParams& p, int64_t pairs, cudaStream_t st) {
+  constexpr size_t smem = Smem<C, W, S, S>::kBytes;
   if constexpr (smem <= kSmemPerSm) {
-    int rc = ensure_smem<eq_fwd_kernel<W, S>>(smem);
+    int rc = ensure_smem<eq_fwd_kernel<C, W, S>>(smem);
     if (rc != DASP_OK) return rc;
-    eq_fwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
+    eq_fwd_kernel<C, W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
     DASP_LAUNCH_OK("eq_fwd_kernel");
     return DASP_OK;
   } else {
@@ -830,30 +868,41 @@ int launch_fwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
     return DASP_ERR_INVALID;
   }
 }
-template <int S>
-int dispatch_fwd(int w, const EqParams& p, int64_t pairs, cudaStream_t st) {
-  switch (w) {
-    case 1: return launch_fwd_w<1, S>(p, pairs, st);
-    case 2: return launch_fwd_w<2, S>(p, pairs, st);
-    case 3: return launch_fwd_w<3, S>(p, pairs, st);
-    case 4: return launch_fwd_w<4, S>(p, pairs, st);
-    case 6: return launch_fwd_w<6, S>(p, pairs, st);
-    default: return launch_fwd_w<8, S>(p, pairs, st);
-  }
-}
-template <int W, int S>
-int launch_bwd_w(const EqParams& p, int64_t pairs, cudaStream_t st) {
-  constexpr size_t smem = Smem<W, BwdUnits<S>::kPerWarp, S>::kBytes;
-  static_assert(smem == bwd_smem(W, S), "shared-memory formula out of sync");
+template <class C, int W, int S>
+int launch_bwd(const EqParams& p, int64_t pairs, cudaStream_t st) {
+  constexpr size_t smem = Smem<C, W, BwdUnits<S>::kPerWarp, S>::kBytes;
   if constexpr (smem <= kSmemPerSm) {
-    int rc = ensure_smem<eq_bwd_kernel<W, S>>(smem);
+    int rc = ensure_smem<eq_bwd_kernel<C, W, S>>(smem);
     if (rc != DASP_OK) return rc;
-    eq_bwd_kernel<W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
+    eq_bwd_kernel<C, W, S><<<(unsigned)pairs, W * 32, smem, st>>>(p);
     DASP_LAUNCH_OK("eq_bwd_kernel");
     return DASP_OK;
   } else {
-    set_error("eq bwd: variant W=%d S=%d needs %zu bytes of shared memory", W, S, smem);
+    set_error("eq bwd: variant W=%d S=%d needs %zu bytes of shared memory (E=%d)", W, S, smem, kE);
     return DASP_ERR_INVALID;
+  }
+}
+template <class C, int S>
+int dispatch_fwd(int w, const EqParams& p, int64_t pairs, cudaStream_t st) {
+  switch (w) {
+    case 1: return launch_fwd<C, 1, S>(p, pairs, st);
+    case 2: return launch_fwd<C, 2, S>(p, pairs, st);
+    case 4: return launch_fwd<C, 4, S>(p, pairs, st);
+    default: return launch_fwd<C, 8, S>(p, pairs, st);
+  }
+}
+template <class C>
+int dispatch_bwd(int w, int stages, const EqParams& p, int64_t pairs, cudaStream_t st) {
+  switch (w * 10 + stages) {
+    case 11: return launch_bwd<C, 1, 1>(p, pairs, st);
+    case 12: return launch_bwd<C, 1, 2>(p, pairs, st);
+    case 21: return launch_bwd<C, 2, 1>(p, pairs, st);
+    case 22: return launch_bwd<C, 2, 2>(p, pairs, st);
+    case 41: return launch_bwd<C, 4, 1>(p, pairs, st);
+    case 42: return launch_bwd<C, 4, 2>(p, pairs, st);
+    case 82: if constexpr (Smem<C, 8, BwdUnits<2>::kPerWarp, 2>::kBytes <= kSmemPerSm) return launch_bwd<C, 8, 2>(p, pairs, st);
+             [[fallthrough]];
+    default: return launch_bwd<C, 8, 1>(p, pairs, st);
   }
 }
 
@@ -880,16 +929,16 @@ int dasp_eq_fwd(const float* x, const float* params, float* y, float* ckpt, int6
   DASP_REQUIRE(sample_rate > 0.f, "eq fwd: sample_rate must be positive");
   const int64_t rows = bs * chs, pairs = (rows + 1) / 2;
   DASP_REQUIRE(pairs < (1ll << 31), "eq fwd: too many rows");
-  int stages = tune_fwd_s() == 1 ? 1 : 2;
-  int w = pick_fwd_warps(pairs, tune_fwd_w());
-  if (fwd_smem(w, stages) > kSmemPerSm) stages = 1;
-  while (w > 1 && fwd_smem(w, stages) > kSmemPerSm) w = (w == 8) ? 6 : (w == 6) ? 4 : (w == 4) ? 3 : w - 1;
+  const int stages = tune_fwd_s() == 1 ? 1 : 2;
+  const int w = pick_fwd_warps(pairs, tune_fwd_w());
   EqParams p{};
   p.x = x; p.y = y; p.params = params; p.ckpt = ckpt; p.n = n; p.rows = rows; p.chs = (int)chs;
   p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;
   p.bulk = (n % 4 == 0) && aligned16(x) && aligned16(y);
   cudaStream_t st = (cudaStream_t)stream;
-  return stages == 1 ? dispatch_fwd<1>(w, p, pairs, st) : dispatch_fwd<2>(w, p, pairs, st);
+  const bool same_item = (chs % 2 == 0) && !tune_force_pair_tables();      // rows 2p and 2p+1 share their item
+  if (same_item) return stages == 1 ? dispatch_fwd<float, 1>(w, p, pairs, st) : dispatch_fwd<float, 2>(w, p, pairs, st);
+  return stages == 1 ? dispatch_fwd<f2, 1>(w, p, pairs, st) : dispatch_fwd<f2, 2>(w, p, pairs, st);
 }
 
 int dasp_eq_bwd(const float* gy, const float* x, const float* params, const float* ckpt, float* gx,
@@ -908,27 +957,14 @@ int dasp_eq_bwd(const float* gy, const float* x, const float* params, const floa
     set_error("eq bwd: workspace needs %lld floats, got %lld", (long long)(rows * 30), (long long)ws_floats);
     return DASP_ERR_WORKSPACE;
   }
-  int stages = tune_bwd_s() == 2 ? 2 : 1;
-  int w = pick_bwd_warps(tune_bwd_w());
-  if (bwd_smem(w, stages) > kSmemPerSm) stages = 1;            // a (W, S) pair that does not fit: fewer stages, then
-  while (w > 1 && bwd_smem(w, stages) > kSmemPerSm) w = (w == 8) ? 6 : (w == 6) ? 4 : (w == 4) ? 3 : w - 1;   // fewer warps
+  const int stages = tune_bwd_s() == 2 ? 2 : 1;
+  const int w = pick_bwd_warps(tune_bwd_w());
   EqParams p{};
   p.x = x; p.gy = gy; p.y = gx; p.params = params; p.ckpt = const_cast<float*>(ckpt); p.partial = ws; p.n = n;
   p.rows = rows; p.chs = (int)chs; p.ntiles = (int)((n + kTile - 1) / kTile); p.sample_rate = sample_rate;
   p.bulk = (n % 4 == 0) && aligned16(x) && aligned16(gy) && aligned16(gx);
-  int rc;
-  switch (w * 10 + stages) {
-    case 11: rc = launch_bwd_w<1, 1>(p, pairs, st); break;
-    case 12: rc = launch_bwd_w<1, 2>(p, pairs, st); break;
-    case 21: rc = launch_bwd_w<2, 1>(p, pairs, st); break;
-    case 22: rc = launch_bwd_w<2, 2>(p, pairs, st); break;
-    case 31: rc = launch_bwd_w<3, 1>(p, pairs, st); break;
-    case 32: rc = launch_bwd_w<3, 2>(p, pairs, st); break;
-    case 41: rc = launch_bwd_w<4, 1>(p, pairs, st); break;
-    case 42: rc = launch_bwd_w<4, 2>(p, pairs, st); break;
-    case 61: rc = launch_bwd_w<6, 1>(p, pairs, st); break;
-    default: rc = launch_bwd_w<8, 1>(p, pairs, st); break;
-  }
+  const bool same_item = (chs % 2 == 0) && !tune_force_pair_tables();
+  const int rc = same_item ? dispatch_bwd<float>(w, stages, p, pairs, st) : dispatch_bwd<f2>(w, stages, p, pairs, st);
   if (rc != DASP_OK) return rc;
   const int64_t tot = bs * kSections;
   eq_param_grad_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(ws, params, gparams, bs, (int)chs, sample_rate);

@@ -43,12 +43,12 @@ constexpr int kPlaneY = 9216;          // floats per plane of the padded buffer 
 constexpr int kTabFloats = 2 * (2 * 64) + 2 * (2 * 512) + 2 * 1024 + 2 * 128;   // see Tables
 
 // ---- packed lane pair ------------------------------------------------------------------------------
-// DASP_FFT_PACKED = 1: the lane pair is one packed fp32x2 register pair (FADD2/FMUL2/FFMA2); 0 (default): the same
-// two lanes as two scalar instructions.  See biquad.cu / profiles/r02_ffma2_probe.md: packed instructions with
-// distinct register-pair operands occupy the FMA pipe almost twice as long as the two scalar ones they replace, and
-// the round-1 FFT kernels sat at that limit (FMA pipe "22 %" by instruction count = ~95 % by pipe cycles).
+// DASP_FFT_PACKED = 1 (default): the lane pair is one packed fp32x2 register pair (FADD2/FMUL2/FFMA2); 0: the same
+// two lanes as two scalar instructions.  A/B on B200 (profiles/r02_eq_variants.md): although a micro-benchmark shows
+// FFMA2 with three distinct register pairs at half the FMA-pipe throughput of two scalar FFMAs (FADD2 is at parity),
+// the packed FFT kernels are 1-6 % FASTER end to end (reverb forward 6.11 vs 6.47 ms), so packed stays.
 #ifndef DASP_FFT_PACKED
-#define DASP_FFT_PACKED 0
+#define DASP_FFT_PACKED 1
 #endif
 #if defined(__CUDA_ARCH__) && DASP_FFT_PACKED
 struct V2 { float2 v; };
