@@ -824,11 +824,11 @@ int tune_bwd_s() {
 // force the general (pair-coefficient) tables even when every pair lies inside one item: test hook via the env
 int tune_force_pair_tables() { static const int v = env_int("DASP_EQ_PAIR_TABLES"); return v; }
 
-// Warps per row pair (W in {1, 2, 4, 8}; 0 / other = automatic).  Measured on B200 at 1024 pairs x 48000 samples
+// Warps per row pair (W in {1, 2, 3, 4, 8}; 0 / other = automatic).  Measured on B200 at 1024 pairs x 48000 samples
 // (profiles/r02_eq_variants.md): forward W=4 with two load stages beats W=2 and the single-wave choices; small batches
 // want W=8 to fill the SMs at all.  The backward holds 255 registers per thread, i.e. 8 warps per SM whatever the
 // split: W=8 with one stage (one CTA per SM, least shared memory per warp) measured best.
-bool valid_w(int w) { return w == 1 || w == 2 || w == 4 || w == 8; }
+bool valid_w(int w) { return w == 1 || w == 2 || w == 3 || w == 4 || w == 8; }
 int pick_fwd_warps(int64_t pairs, int tuned) {
   const int f = debug_forced_warps() ? debug_forced_warps() : tuned;
   if (valid_w(f)) return f;
@@ -887,6 +887,7 @@ int dispatch_fwd(int w, const EqParams& p, int64_t pairs, cudaStream_t st) {
   switch (w) {
     case 1: return launch_fwd<C, 1, S>(p, pairs, st);
     case 2: return launch_fwd<C, 2, S>(p, pairs, st);
+    case 3: return launch_fwd<C, 3, S>(p, pairs, st);
     case 4: return launch_fwd<C, 4, S>(p, pairs, st);
     default: return launch_fwd<C, 8, S>(p, pairs, st);
   }
@@ -898,6 +899,8 @@ int dispatch_bwd(int w, int stages, const EqParams& p, int64_t pairs, cudaStream
     case 12: return launch_bwd<C, 1, 2>(p, pairs, st);
     case 21: return launch_bwd<C, 2, 1>(p, pairs, st);
     case 22: return launch_bwd<C, 2, 2>(p, pairs, st);
+    case 31: return launch_bwd<C, 3, 1>(p, pairs, st);
+    case 32: return launch_bwd<C, 3, 2>(p, pairs, st);
     case 41: return launch_bwd<C, 4, 1>(p, pairs, st);
     case 42: return launch_bwd<C, 4, 2>(p, pairs, st);
     case 82: if constexpr (Smem<C, 8, BwdUnits<2>::kPerWarp, 2>::kBytes <= kSmemPerSm) return launch_bwd<C, 8, 2>(p, pairs, st);
