@@ -211,11 +211,15 @@ def cpu_arm(budget_s, warm=True):
     allows; returns (samples/s at the largest batch finished, detail dict).
 
     Thread count: torchrun exports OMP_NUM_THREADS=1 and a 128-core box is NOT fastest with 128 intra-op threads (the
-    reference's grouped conv1d collapses there: 372 s for 4 items in round 2's first run, against ~25 s with 32
-    threads), so a one-item pass is timed at 32 threads and at all cores and the faster setting is kept -- the reference
-    gets the best configuration found, and `cores` reports it."""
+    reference's grouped conv1d collapses there: 93 s per item in round 2's first run, 23 s with 32 threads), so a
+    one-item pass is timed at 8, 16, 32, ... threads until more threads stop helping and the fastest setting is kept --
+    the reference gets the best configuration found, and `cores` reports it."""
     import torch
     ncpu = os.cpu_count() or 1
+    try:
+        ncpu = min(ncpu, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     ref = load_reference()
     if ref is not None:
         mod, kind, kw = ref, "reference", {}
@@ -224,11 +228,11 @@ def cpu_arm(budget_s, warm=True):
         mod, kind, kw = oracle, "port", {"method": "direct"}
     t_start = time.perf_counter()
     cal = {}
-    for t in sorted({min(32, ncpu), ncpu}):
+    for t in [c for c in (8, 16, 32, 64, 128) if c <= ncpu] or [ncpu]:
         torch.set_num_threads(t)
         cal[t] = reference_chain_seconds(mod, 1, "cpu", kw)   # doubles as the warm-up pass (thread pools, scipy firwin)
-        if cal[t] > 0.25 * budget_s:
-            break
+        if cal[t] > 1.15 * min(cal.values()) or (time.perf_counter() - t_start) > 0.3 * budget_s:
+            break                                             # more threads stopped helping (or the budget is going)
     best_t = min(cal, key=lambda k: cal[k])
     torch.set_num_threads(best_t)
     rates, times = {1: CHS * N_SAMPLES / cal[best_t]}, {1: cal[best_t]}
