@@ -50,6 +50,12 @@ constexpr int kTabFloats = 2 * (2 * 64) + 2 * (2 * 512) + 2 * 1024 + 2 * 128;   
 #ifndef DASP_FFT_PACKED
 #define DASP_FFT_PACKED 1
 #endif
+// DASP_FFT_TWIDDLE_RECURRENCE = 1 (default): the seven twiddles a thread needs in a pass are successive powers of one
+// table entry, formed by complex multiplication in registers instead of being fetched one by one -- the FFT kernels are
+// bound by the shared-memory pipe (data exchange + twiddle fetches), not by the FMA pipe (profiles/r02_reverb_*.md).
+#ifndef DASP_FFT_TWIDDLE_RECURRENCE
+#define DASP_FFT_TWIDDLE_RECURRENCE 1
+#endif
 #if defined(__CUDA_ARCH__) && DASP_FFT_PACKED
 struct V2 { float2 v; };
 DASP_HD V2 v2(float a, float b) { V2 r; r.v = make_float2(a, b); return r; }
@@ -185,8 +191,20 @@ DASP_HD void p1(float* gr, float* gi, const Tables& tb, int t) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) { r[j] = ld2(gr + 1024 * j + m); i[j] = ld2(gi + 1024 * j + m); }
   dft8<INV>(r, i);
+#if DASP_FFT_TWIDDLE_RECURRENCE
+  {  // w64^(n2 k1) = (w64^n2)^k1: one table entry, six complex multiplies instead of six more (pairs of) loads
+    const V2 w1r = ld2(tb.w64b_c + 2 * n2), w1i = ld2(tb.w64b_s + 2 * n2);
+    V2 wr = w1r, wi = w1i;
+#pragma unroll
+    for (int k1 = 1; k1 < 8; ++k1) {
+      cmul<INV>(r[k1], i[k1], wr, wi);
+      if (k1 < 7) cmul<true>(wr, wi, w1r, w1i);
+    }
+  }
+#else
 #pragma unroll
   for (int k1 = 1; k1 < 8; ++k1) cmul<INV>(r[k1], i[k1], ld2(tb.w64b_c + 2 * (n2 * k1)), ld2(tb.w64b_s + 2 * (n2 * k1)));
+#endif
 #pragma unroll
   for (int k1 = 0; k1 < 8; ++k1) { st2(gr + 1024 * k1 + m, r[k1]); st2(gi + 1024 * k1 + m, i[k1]); }
 }
@@ -199,12 +217,24 @@ DASP_HD void p2(const float* gr, const float* gi, float* yr, float* yi, const Ta
 #pragma unroll
   for (int n2 = 0; n2 < 8; ++n2) { r[n2] = ld2(gr + src + 128 * n2); i[n2] = ld2(gi + src + 128 * n2); }
   dft8<INV>(r, i);
+#if DASP_FFT_TWIDDLE_RECURRENCE
+  // w512^(n3 (k1 + 8 k2)) = w512^(n3 k1) * (w64^n3)^k2: two table entries and seven complex multiplies
+  V2 wr = ld2(tb.w512b_c + 2 * (n3 * k1)), wi = ld2(tb.w512b_s + 2 * (n3 * k1));
+  const V2 sr = ld2(tb.w64b_c + 2 * n3), si = ld2(tb.w64b_s + 2 * n3);
+#pragma unroll
+  for (int k2 = 0; k2 < 8; ++k2) {
+    cmul<INV>(r[k2], i[k2], wr, wi);
+    st2(yr + dst + 144 * k2, r[k2]); st2(yi + dst + 144 * k2, i[k2]);
+    if (k2 < 7) cmul<true>(wr, wi, sr, si);
+  }
+#else
 #pragma unroll
   for (int k2 = 0; k2 < 8; ++k2) {
     const int e = n3 * (k1 + 8 * k2);
     cmul<INV>(r[k2], i[k2], ld2(tb.w512b_c + 2 * e), ld2(tb.w512b_s + 2 * e));
     st2(yr + dst + 144 * k2, r[k2]); st2(yi + dst + 144 * k2, i[k2]);
   }
+#endif
 }
 
 struct P3Regs { V2 r[8], i[8]; };
@@ -222,6 +252,18 @@ DASP_HD void p3_store(float* yr, float* yi, const Tables& tb, int t, P3Regs& q) 
   dft8<INV>(q.r, q.i);
   const int qq = k1 + 8 * k2, n4a = 2 * j, n4b = 2 * j + 1;
   const V2 bwr = v2(tb.w8k_c[n4a * qq], tb.w8k_c[n4b * qq]), bwi = v2(tb.w8k_s[n4a * qq], tb.w8k_s[n4b * qq]);
+#if DASP_FFT_TWIDDLE_RECURRENCE
+  // w8192^(n4 (qq + 64 k3)) = w8192^(n4 qq) * (w128^n4)^k3: the same multiply count as before, 24 fewer scalar loads
+  const V2 sr = v2(tb.w128_c[n4a], tb.w128_c[n4b]), si = v2(tb.w128_s[n4a], tb.w128_s[n4b]);
+  V2 wr = bwr, wi = bwi;
+#pragma unroll
+  for (int k3 = 0; k3 < 8; ++k3) {
+    cmul<INV>(q.r[k3], q.i[k3], wr, wi);
+    const int dst = 18 * (qq + 64 * k3) + 2 * j;
+    st2(yr + dst, q.r[k3]); st2(yi + dst, q.i[k3]);
+    if (k3 < 7) cmul<true>(wr, wi, sr, si);
+  }
+#else
 #pragma unroll
   for (int k3 = 0; k3 < 8; ++k3) {
     V2 wr = bwr, wi = bwi;
@@ -233,6 +275,7 @@ DASP_HD void p3_store(float* yr, float* yi, const Tables& tb, int t, P3Regs& q) 
     const int dst = 18 * (qq + 64 * k3) + 2 * j;
     st2(yr + dst, q.r[k3]); st2(yi + dst, q.i[k3]);
   }
+#endif
 }
 
 // out_r[k4], out_i[k4] = X[t + 512 k4]

@@ -56,7 +56,9 @@ def full(src, dst, note=""):
             ("DRAM %", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
             ("SM %", "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
             ("issue %", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
-            ("FMA pipe %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            ("FMA pipe inst %", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            ("FMA pipe cycles %", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+            ("smem/shuffle pipe %", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
             ("XU pipe %", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
             ("warps active %", "sm__warps_active.avg.pct_of_peak_sustained_active"),
             ("regs", "launch__registers_per_thread"), ("L2 %", "lts__throughput.avg.pct_of_peak_sustained_elapsed")]
@@ -79,7 +81,41 @@ def full(src, dst, note=""):
                     " | ".join(f"{g(d, k):.1f}" for _, k in want) + " | " + ", ".join(f"{n} {v:.2f}" for v, n in st) + " |\n")
 
 
+def traffic(src, dst, note=""):
+    """profiles/r02_traffic.json: DRAM bytes per item of the reverb's forward and backward pipelines, summed over the
+    kernels of one `ncu --set full` capture of tools/debug/reverb_step.py <items> (bench.py reads this file)"""
+    import json
+    raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, data = rows[0], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    units = rows[1]
+    fwd_names = ("spectral_gen", "ifft_shape", "x_fft", "ifft_mix", "vector_fft", "regular_fft")
+    tot = {"reverb_fwd": 0.0, "reverb_bwd": 0.0}
+    per_kernel = []
+    seen_bwd = False
+    for d in data:
+        name = d[idx["Kernel Name"]]
+        b = sum(float(d[idx[k]].replace(",", "")) * scale.get(units[idx[k]], 1.0)
+                for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        if "g_fft" in name:
+            seen_bwd = True
+        is_fwd = (not seen_bwd) and (any(f in name for f in fwd_names) or "partition_mac" in name)
+        tot["reverb_fwd" if is_fwd else "reverb_bwd"] += b
+        per_kernel.append({"kernel": short(name), "dir": "fwd" if is_fwd else "bwd", "dram_bytes": b,
+                           "us": float(d[idx["gpu__time_duration.sum"]].replace(",", ""))})
+    items = int(note) if note else 148
+    out = {"geometry": [48000, 96000, 1023], "items_in_capture": items,
+           "dram_bytes_per_item": {k: v / items for k, v in tot.items()},
+           "source": f"{src} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the "
+                     "kernels of one chunk; tools/summarize_profiles.py traffic)", "kernels": per_kernel}
+    with open(dst, "w") as f:
+        json.dump(out, f, indent=1)
+    print(json.dumps(out["dram_bytes_per_item"]))
+
+
 if __name__ == "__main__":
     mode, src, dst = sys.argv[1:4]
     note = sys.argv[4] if len(sys.argv) > 4 else ""
-    (launches if mode == "launches" else full)(src, dst, note)
+    {"launches": launches, "full": full, "traffic": traffic}[mode](src, dst, note)
