@@ -26,7 +26,10 @@
 namespace dasp {
 namespace {
 
-constexpr int kE = 7;        // samples per thread per tile; odd => stride-E smem access is conflict-free
+#ifndef DASP_DYN_E
+#define DASP_DYN_E 7
+#endif
+constexpr int kE = DASP_DYN_E;        // samples per thread per tile; odd => stride-E smem access is conflict-free
 constexpr int kStages = 3;
 constexpr int kMaxChs = 32;
 constexpr float kDbPerLog2 = 6.020599913279624f;    // 20*log10(2)

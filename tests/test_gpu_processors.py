@@ -19,6 +19,11 @@ def test_process_normalized_fast_path_matches_functional(cuda_device):
     cols = [q.to(cuda_device) for q in denorm(p.detach().cpu(), eq_ranges())]
     y_ref = D.parametric_eq(x, SR, *cols)
     assert torch.allclose(y, y_ref, rtol=1e-4, atol=1e-5)
+    # ... and against the oracle fed the reference's own denormalisation (modules.py:13-14) of the same tensor
+    import oracle
+    from helpers import peak_err
+    y_orc = oracle.parametric_eq(x.detach().cpu().double(), SR, *[c.cpu().double() for c in cols], fsm_tail=1 << 16)
+    assert peak_err(y.detach().cpu(), y_orc).max() < 1e-4
     y.pow(2).mean().backward()
     assert p.grad is not None and p.grad.shape == (bs, 18) and bool(p.grad.abs().sum() > 0)
     # compressor (release column receives zero gradient: unused upstream)

@@ -44,7 +44,14 @@ def main():
             continue
         d = demangle(name)
         d = re.sub(r"\(anonymous namespace\)::", "", d)
-        d = re.sub(r"\(.*\)$", "", d)
+        if d.endswith(")"):                      # drop the trailing parameter list (balanced parentheses from the end)
+            depth = 0
+            for i in range(len(d) - 1, -1, -1):
+                depth += d[i] == ")"
+                depth -= d[i] == "("
+                if depth == 0:
+                    d = d[:i]
+                    break
         if md:
             print(f"| `{d}` | {c['_total']} | " + " | ".join(str(c[k]) for k in KEYS) + " |")
         else:
