@@ -268,8 +268,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys& ks) {
 // MUFU-only transcendental path (lg2, rsq, sin, cos: |abs err| ~ 1e-6, irrelevant for a noise source) -- the
 // generator kernel is instruction-issue bound and the accurate logf/sqrtf/sincospif were ~55 % of it
 __device__ __forceinline__ float2 box_muller(unsigned a, unsigned b) {
-  const float u1 = ((float)a + 1.0f) * 2.3283064365386963e-10f;       // (a+1) / 2^32, rounds into (0, 1]
-  const float ang = ((float)b * 2.3283064365386963e-10f - 0.5f) * 6.283185307179586f;   // [-pi, pi)
+  // uniforms from the top 23 bits placed in the mantissa of [1, 2): no I2F (the conversions share the XU pipe with the
+  // four MUFU calls below).  u1 = 2 - [1,2) lies in (0, 1]; the angle (v - 1.5) * 2 pi in [-pi, pi)
+  const float u1 = 2.0f - __uint_as_float(0x3f800000u | (a >> 9));
+  const float ang = fmaf(__uint_as_float(0x3f800000u | (b >> 9)), 6.283185307179586f, -9.42477796076938f);
   const float m = -2.0f * __logf(u1);                                  // >= 0
   const float r = m * rsqrtf(fmaxf(m, 1e-30f));                        // sqrt(m)
   return make_float2(r * __cosf(ang), r * __sinf(ang));
@@ -285,7 +287,9 @@ template <int R, class Emit>
 __device__ __forceinline__ void spectral_unit(int j1, int nb, const float2* __restrict__ h, unsigned long long pair,
                                               const PhiloxKeys& keys, Emit&& emit) {
   const int n1 = R * nb, n1h = n1 / 2;
-  const float s_half = sqrtf(0.5f * (float)n1), s_full = sqrtf((float)n1);
+  // the real-valued bins 0 and n1/2 (variance n1 on the real axis instead of n1/2 per component) only occur in the two
+  // self-mirrored classes j1 = 0 and j1 = nb/2: everything else takes the branch-free path
+  const bool special_unit = (j1 == 0) || (2 * j1 == nb);
   // value of the packed spectrum G_left + i G_right at bin j (0 <= j < n1) and at its mirror n1 - j
   // `canonical` (j <= n1/2) is a compile-time fact of the unrolled call site: for j1 in [0, nb/2] the bin
   // j1 + nb j2 lies in the lower half exactly when 2 j2 < R (the only tie, j = n1/2, is its own mirror)
@@ -293,11 +297,12 @@ __device__ __forceinline__ void spectral_unit(int j1, int nb, const float2* __re
     const int jc = canonical ? j : n1 - j;
     // counter = (canonical bin, band pair), key = seed: one Philox block -> both channels' complex Gaussian
     const uint4 rnd = philox4x32_10(make_uint4((unsigned)jc, (unsigned)pair, (unsigned)(pair >> 32), 0x5eedu), keys);
-    const float2 nl = box_muller(rnd.x, rnd.y), nr = box_muller(rnd.z, rnd.w);
-    float2 zl, zr;
-    if (jc == 0 || jc == n1h) { zl = make_float2(nl.x * s_full, 0.f); zr = make_float2(nr.x * s_full, 0.f); }
-    else { zl = make_float2(nl.x * s_half, nl.y * s_half); zr = make_float2(nr.x * s_half, nr.y * s_half); }
-    const float2 w = h[jc];
+    float2 zl = box_muller(rnd.x, rnd.y), zr = box_muller(rnd.z, rnd.w);
+    if (special_unit && (jc == 0 || jc == n1h)) {
+      zl = make_float2(zl.x * 1.4142135623730951f, 0.f);
+      zr = make_float2(zr.x * 1.4142135623730951f, 0.f);
+    }
+    const float2 w = h[jc];                                          // H_k / n1 * sqrt(n1 / 2), folded on the host
     const float2 sl = make_float2(w.x * zl.x - w.y * zl.y, w.x * zl.y + w.y * zl.x);   // H Z_left
     const float2 sr = make_float2(w.x * zr.x - w.y * zr.y, w.x * zr.y + w.y * zr.x);   // H Z_right
     const float2 canon = make_float2(sl.x - sr.y, sl.y + sr.x);      // S_l + i S_r           (bin jc)
@@ -326,22 +331,59 @@ __device__ __forceinline__ void spectral_unit(int j1, int nb, const float2* __re
   }
   // per-class twiddle steps e^{2 pi i j1 / n1} and e^{2 pi i (nb - j1) / n1} = e^{2 pi i / R} conj(the former)
   float2 w1a, w1b;
-  sincospif(2.0f * (float)j1 / (float)n1, &w1a.y, &w1a.x);
+  __sincosf(6.283185307179586f * (float)j1 / (float)n1, &w1a.y, &w1a.x);      // argument <= pi / R
   {
     const float2 r1 = (R == 1) ? make_float2(1.f, 0.f) : c_root[R][1 % R];
     w1b = make_float2(fmaf(r1.x, w1a.x, r1.y * w1a.y), fmaf(r1.y, w1a.x, -r1.x * w1a.y));
   }
   const float2 wx = make_float2(w1a.x, w1b.x), wy = make_float2(w1a.y, w1b.y), nwy = make_float2(-w1a.y, -w1b.y);
   float2 tx = make_float2(1.f, 1.f), ty = make_float2(0.f, 0.f);      // twiddle e^{2 pi i j b / n1}, both classes
+  // S[b] = sum_{j2} g[j2] e^{+2 pi i j2 b / R}: generic O(R^2) form, or for R = 6 (IR 96000 on 48000 samples, the
+  // BASELINE geometry) radix 2 x 3 with literal constants -- 48 packed operations instead of 144
+  float2 Sre[R], Sim[R];
+  if constexpr (R == 6) {
+    const float2 hlf = make_float2(0.5f, 0.5f), nhlf = make_float2(-0.5f, -0.5f);
+    const float2 c3 = make_float2(0.8660254037844386f, 0.8660254037844386f), nc3 = make_float2(-0.8660254037844386f, -0.8660254037844386f);
+    const float2 one = make_float2(1.f, 1.f), mone = make_float2(-1.f, -1.f);
+    auto add = [&](float2 a, float2 b) { return gen_ffma2(b, one, a); };
+    auto sub = [&](float2 a, float2 b) { return gen_ffma2(b, mone, a); };
+    // 3-point DFT (positive exponent) of (a0, a1, a2): Y0 = a0 + t, Y1/2 = (a0 - t/2) +- i (sqrt3/2) d
+    auto dft3 = [&](float2 a0r, float2 a0i, float2 a1r, float2 a1i, float2 a2r, float2 a2i, float2 (&yr)[3], float2 (&yi)[3]) {
+      const float2 tr = add(a1r, a2r), ti = add(a1i, a2i), dr = sub(a1r, a2r), di = sub(a1i, a2i);
+      yr[0] = add(a0r, tr); yi[0] = add(a0i, ti);
+      const float2 mr = gen_ffma2(tr, nhlf, a0r), mi = gen_ffma2(ti, nhlf, a0i);
+      yr[1] = gen_ffma2(di, nc3, mr); yi[1] = gen_ffma2(dr, c3, mi);       // + i c d = (-c d_i, c d_r)
+      yr[2] = gen_ffma2(di, c3, mr);  yi[2] = gen_ffma2(dr, nc3, mi);
+    };
+    float2 er[3], ei[3], orr[3], oi[3];
+    dft3(gx[0], gy[0], gx[2], gy[2], gx[4], gy[4], er, ei);
+    dft3(gx[1], gy[1], gx[3], gy[3], gx[5], gy[5], orr, oi);
+    // X[k] = E[k] + W6^k O[k], X[k+3] = E[k] - W6^k O[k];  W6 = (1/2, sqrt3/2), W6^2 = (-1/2, sqrt3/2)
+    float2 pr[3], pi[3];
+    pr[0] = orr[0]; pi[0] = oi[0];
+    pr[1] = gen_ffma2(orr[1], hlf, gen_fmul2(oi[1], nc3));  pi[1] = gen_ffma2(orr[1], c3, gen_fmul2(oi[1], hlf));
+    pr[2] = gen_ffma2(orr[2], nhlf, gen_fmul2(oi[2], nc3)); pi[2] = gen_ffma2(orr[2], c3, gen_fmul2(oi[2], nhlf));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      Sre[k] = add(er[k], pr[k]); Sim[k] = add(ei[k], pi[k]);
+      Sre[k + 3] = sub(er[k], pr[k]); Sim[k + 3] = sub(ei[k], pi[k]);
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < R; ++b) {
+      float2 sre = make_float2(0.f, 0.f), sim = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j2 = 0; j2 < R; ++j2) {
+        const int m = (j2 * b) % R;
+        sre = gen_ffma2(gx[j2], rx[m], gen_ffma2(gy[j2], nry[m], sre));
+        sim = gen_ffma2(gx[j2], ry[m], gen_ffma2(gy[j2], rx[m], sim));
+      }
+      Sre[b] = sre; Sim[b] = sim;
+    }
+  }
 #pragma unroll
   for (int b = 0; b < R; ++b) {
-    float2 sre = make_float2(0.f, 0.f), sim = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int j2 = 0; j2 < R; ++j2) {
-      const int m = (j2 * b) % R;
-      sre = gen_ffma2(gx[j2], rx[m], gen_ffma2(gy[j2], nry[m], sre));
-      sim = gen_ffma2(gx[j2], ry[m], gen_ffma2(gy[j2], rx[m], sim));
-    }
+    const float2 sre = Sre[b], sim = Sim[b];
     const float2 ore = gen_ffma2(sre, tx, gen_fmul2(sim, make_float2(-ty.x, -ty.y)));
     const float2 oim = gen_ffma2(sre, ty, gen_fmul2(sim, tx));
     emit(b, make_float2(ore.x, oim.x), make_float2(ore.y, oim.y));
@@ -1419,7 +1461,7 @@ int get_filterbank(const Geom& g, double sr, cudaStream_t st, const float2** out
   return DASP_OK;
 }
 
-// half spectrum of the taps on the n1-point grid of the spectral synthesis: 12 x (n1/2+1) complex, scaled 1/n1
+// half spectrum of the taps on the n1-point grid of the spectral synthesis: 12 x (n1/2+1) complex, scaled sqrt(n1/2)/n1
 int get_filterbank_n1(const Geom& g, double sr, cudaStream_t st, const float2** out) {
   int dev = 0;
   DASP_CUDA_OK(cudaGetDevice(&dev));
@@ -1446,7 +1488,8 @@ int get_filterbank_n1(const Geom& g, double sr, cudaStream_t st, const float2** 
     for (int k = 0; k < kBands; ++k) taps[(size_t)k * g.taps] = 1.0f;      // unit impulse at lag 0
   }
   std::vector<float> padded((size_t)kBands * n1, 0.f);
-  const float inv = 1.0f / (float)n1;
+  // 1/n1 of the inverse transform and the sqrt(n1/2) of the bins' complex Gaussians (Z ~ CN(0, n1)) are folded in
+  const float inv = (float)(sqrt(0.5 * (double)n1) / (double)n1);
   for (int k = 0; k < kBands; ++k)
     for (int64_t i = 0; i < g.taps; ++i) padded[(size_t)k * n1 + i] = taps[(size_t)k * g.taps + i] * inv;
   float* d_in = nullptr;
