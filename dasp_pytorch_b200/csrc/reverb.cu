@@ -1280,6 +1280,52 @@ __global__ void __launch_bounds__(128) partition_mac_kernel(const float2* __rest
   }
 }
 
+// Both correlation products of the backward in ONE pass over the gradient spectra (each was HBM bound on its own):
+//   D[q] = sum_{j<J, q+j<I} G[q+j] conj(H[j])  (q < I)   dL/dx windows
+//   E[j] = sum_{p<I, j+p<I} G[j+p] conj(X[p])  (j < J)   dL/dIR partitions
+// G is read and untangled once; H and X take turns in the same registers.  Planar outputs (own inverse FFT kernels).
+template <int MAXB>
+__global__ void __launch_bounds__(128) partition_mac_bwd_kernel(const float2* __restrict__ G, const float2* __restrict__ H,
+                                                                const float2* __restrict__ X, float2* __restrict__ D,
+                                                                float2* __restrict__ E, int I, int J, float scale) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > kNbA / 2) return;
+  const int fm = (kNbA - f) & (kNbA - 1);
+  const int64_t il = blockIdx.y;
+  const float2* g = G + il * (int64_t)I * kNbA;
+  float2 al[MAXB], ar[MAXB], bl[MAXB], br[MAXB];
+#pragma unroll
+  for (int i = 0; i < MAXB; ++i) {
+    al[i] = ar[i] = make_float2(0.f, 0.f);
+    if (i < I) untangle(g[(int64_t)i * kNbA + f], g[(int64_t)i * kNbA + fm], al[i], ar[i]);
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const float2* bq = (pass == 0 ? H + il * (int64_t)J * kNbA : X + il * (int64_t)I * kNbA);
+    const int nbm = pass == 0 ? J : I, nout = pass == 0 ? I : J;
+    float2* out = (pass == 0 ? D + il * (int64_t)I * kNbA : E + il * (int64_t)J * kNbA);
+#pragma unroll
+    for (int i = 0; i < MAXB; ++i) {
+      bl[i] = br[i] = make_float2(0.f, 0.f);
+      if (i < nbm) untangle(bq[(int64_t)i * kNbA + f], bq[(int64_t)i * kNbA + fm], bl[i], br[i]);
+    }
+#pragma unroll
+    for (int o = 0; o < MAXB; ++o) {
+      if (o < nout) {
+        float2 sl = make_float2(0.f, 0.f), sr = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < MAXB; ++j) {
+          if (o + j < MAXB) { cfma_conj(sl, al[o + j], bl[j]); cfma_conj(sr, ar[o + j], br[j]); }   // operands beyond I / nbm are zero
+        }
+        sl.x *= scale; sl.y *= scale; sr.x *= scale; sr.y *= scale;
+        float* pl = reinterpret_cast<float*>(out + (int64_t)o * kNbA);
+        pl[f] = sl.x - sr.y; pl[kNbA + f] = sl.y + sr.x;
+        if (fm != f) { pl[fm] = sl.x + sr.y; pl[kNbA + fm] = sr.x - sl.y; }
+      }
+    }
+  }
+}
+
 // y = (1-mix) x + mix wet; wet[n] = Yt[(il*I + n/kB)*kNbA + kB + n%kB]; also saves wet for the backward
 __global__ void mix_blocks_kernel(const float* __restrict__ x, const float2* __restrict__ Yt,
                                   const float* __restrict__ params, float* __restrict__ y, float* __restrict__ wet_save,
@@ -1935,12 +1981,21 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
     }
     const int nblk = (int)(items * I);
     const unsigned fft_grid = (unsigned)(nblk < sm_count() ? nblk : sm_count());
+    const int mb = I > J ? I : J;
+    const bool fused_mac = own_irgrad && mb <= 16;
     if (own_conv) {
       g_fft_kernel<<<fft_grid, kFusedThreads, kFftSmemBytes, st>>>(gy, x, wet_save, params, ws_gs, ws_mixpart, tw, item0, I, n,
                                                                    (int)in_chs, nblk);
       DASP_LAUNCH_OK("g_fft_kernel");
-      launch_mac<true, true>(ws_gs, hs, ws_ds, I, J, I, items, inv, st);      // dx windows: sum_j conj(H[j]) G[q+j]
-      DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+      if (fused_mac) {
+        dim3 mgrid((kNbA / 2 + 1 + 127) / 128, (unsigned)items);
+        if (mb <= 12) partition_mac_bwd_kernel<12><<<mgrid, 128, 0, st>>>(ws_gs, hs, xs, ws_ds, ws_es, I, J, inv);
+        else          partition_mac_bwd_kernel<16><<<mgrid, 128, 0, st>>>(ws_gs, hs, xs, ws_ds, ws_es, I, J, inv);
+        DASP_LAUNCH_OK("partition_mac_bwd_kernel");
+      } else {
+        launch_mac<true, true>(ws_gs, hs, ws_ds, I, J, I, items, inv, st);      // dx windows: sum_j conj(H[j]) G[q+j]
+        DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+      }
       const unsigned dx_grid = (unsigned)(items < sm_count() ? items : sm_count());
       ifft_dx_kernel<<<dx_grid, kFusedThreads, kFftSmemBytes, st>>>(reinterpret_cast<const float*>(ws_ds), tw, gy, params, gx,
                                                                     item0, (int)items, I, n, (int)in_chs);
@@ -1961,8 +2016,10 @@ int dasp_reverb_bwd(const float* gy, const float* x, int64_t in_chs, const float
     }
     int nparts;
     if (own_irgrad) {
-      launch_mac<true, true>(ws_gs, xs, ws_es, I, I, J, items, inv, st);      // dIR partitions: sum_p conj(X[p]) G[j+p]
-      DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+      if (!fused_mac) {
+        launch_mac<true, true>(ws_gs, xs, ws_es, I, I, J, items, inv, st);      // dIR partitions: sum_p conj(X[p]) G[j+p]
+        DASP_LAUNCH_OK("partition_mac_kernel<corr>");
+      }
       nparts = J;
       const int nunits = (int)(items * J);
       const unsigned ig_grid = (unsigned)(nunits < sm_count() ? nunits : sm_count());
