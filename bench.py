@@ -388,8 +388,9 @@ class Step:
 def own_launches_per_step(bs, chunk_items):
     chunks = -(-bs // chunk_items)
     # eq fwd 1, bwd 2; compressor fwd 1, bwd 1; distortion fwd 1, bwd 2; reverb per chunk: fwd 5 (spectral_gen,
-    # ifft_shape, x_fft, partition_mac, ifft_mix), bwd 6 (g_fft, partition_mac x2, ifft_dx, ifft_irgrad, param_grad)
-    return 1 + 2 + 1 + 1 + 1 + 2 + chunks * (5 + 6)
+    # ifft_shape, x_fft, partition_mac, ifft_mix), bwd 5 (g_fft, partition_mac_bwd, ifft_dx, ifft_irgrad, param_grad)
+    # (+ one cuFFT launch per chunk for the IR partitions, not counted: library kernel)
+    return 1 + 2 + 1 + 1 + 1 + 2 + chunks * (5 + 5)
 
 
 def bench_configs(D, F, dev, peak):

@@ -108,8 +108,9 @@ def traffic(src, dst, note=""):
     items = int(note) if note else 148
     out = {"geometry": [48000, 96000, 1023], "items_in_capture": items,
            "dram_bytes_per_item": {k: v / items for k, v in tot.items()},
-           "source": f"{src} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over the "
-                     "kernels of one chunk; tools/summarize_profiles.py traffic)", "kernels": per_kernel}
+           "source": f"profiles/r02_reverb_kernels_b148_full.md / {src.split('/')[-1]} (ncu --set full, dram__bytes_read.sum + "
+                     "dram__bytes_write.sum per launch, summed over the kernels of one 148-item chunk of "
+                     "tools/debug/reverb_step.py; tools/summarize_profiles.py traffic)", "kernels": per_kernel}
     with open(dst, "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out["dram_bytes_per_item"]))
