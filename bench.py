@@ -608,6 +608,25 @@ def main():
     d2h = 4 + bs * 49 * 4 + bs * CHS * 4
 
     extras = {}
+    if world > 1:
+        # cross-GPU self-check (the driver's pytest box has one GPU, so tests/test_gpu_multi.py is skipped there): every
+        # rank runs eq -> compressor -> distortion fwd+bwd on the SAME small seeded batch; outputs and gradients must be
+        # bit-identical on all GPUs (items are independent, no atomics, fixed reduction orders)
+        gchk = torch.Generator().manual_seed(4242)
+        xc = (torch.rand(6, CHS, 6000, generator=gchk) * 2 - 1).to(dev).requires_grad_(True)
+        pc01 = torch.rand(6, 24, generator=gchk)
+        pc01[:, 22].clamp_(min=0.05)
+        lo = torch.tensor([r[0] for r in eq_ranges() + COMP_RANGES]); hi = torch.tensor([r[1] for r in eq_ranges() + COMP_RANGES])
+        pc = (pc01 * (hi - lo) + lo).to(dev).requires_grad_(True)
+        dc = (torch.rand(12, generator=gchk) * 24).to(dev)
+        cols = pc.unbind(1)
+        yc = D.distortion(D.compressor(D.parametric_eq(xc, SR, *cols[:18]), SR, *cols[18:24]), SR, dc)
+        yc.pow(2).mean().backward()
+        sig = torch.cat([yc.detach().reshape(-1), xc.grad.reshape(-1), pc.grad.reshape(-1)]).contiguous()
+        allsig = [torch.empty_like(sig) for _ in range(world)]
+        dist.all_gather(allsig, sig)
+        extras["cross_gpu_bit_identity"] = bool(all(torch.equal(a, allsig[0]) for a in allsig))
+        del xc, pc, yc
     if world > 1 and not args.no_extras:
         # ---- (a) the NCCL edges for a caller that holds the whole batch on rank 0: scatter x / params / drive,
         #      gather y; timed separately from the compute, device events, max over ranks ----
