@@ -19,6 +19,7 @@
 // w[n] = ds[n] + a w[n+1] with the mirrored scan (shfl_down), accumulates the five parameter
 // gradients in registers across tiles (deterministic), and writes dL/dx in place.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tile_pipe.cuh"
@@ -254,7 +255,10 @@ struct Smem {
 constexpr size_t kSmemHeader = 256;
 
 // =============================================================================== forward
-template <Curve CV, int W, bool LA>     // LA: lookahead_samples > 0 (rare; kept out of the common instantiation)
+// LA: lookahead_samples > 0 (rare; kept out of the common instantiation).  ST: stereo specialisation (C == 2, no
+// look-ahead): the two channel values of a sample stay in registers between the side-chain sum and the gain application
+// instead of being read from shared memory twice (round 2: the scan kernels are bound by the shared-memory pipe).
+template <Curve CV, int W, bool LA, bool ST = false>
 __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<W> sm(smem_raw);
@@ -284,14 +288,22 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
 
     // side chain + static curve + zero-state local pass
     float s[kE];
+    float x0[ST ? kE : 1], x1[ST ? kE : 1];
     {
       float xs[kE];
+      if (ST) {
+        const float* xa = pipe.buf(st, 0) + off;
+        const float* xb = pipe.buf(st, 1) + off;
 #pragma unroll
-      for (int j = 0; j < kE; ++j) xs[j] = 0.f;
-      for (int c = 0; c < C; ++c) {
-        const float* xb = pipe.buf(st, c) + off;
+        for (int j = 0; j < kE; ++j) { x0[ST ? j : 0] = xa[j]; x1[ST ? j : 0] = xb[j]; xs[j] = xa[j] + xb[j]; }
+      } else {
 #pragma unroll
-        for (int j = 0; j < kE; ++j) xs[j] += xb[j];
+        for (int j = 0; j < kE; ++j) xs[j] = 0.f;
+        for (int c = 0; c < C; ++c) {
+          const float* xb = pipe.buf(st, c) + off;
+#pragma unroll
+          for (int j = 0; j < kE; ++j) xs[j] += xb[j];
+        }
       }
       float run = 0.f;
 #pragma unroll
@@ -308,7 +320,12 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
     float G[kE];
 #pragma unroll
     for (int j = 0; j < kE; ++j) G[j] = exp2f((fmaf(tb.apow[j], c_in, s[j]) + M) * kLog2Of10Over20);
-    if (!LA) {
+    if (ST) {
+      float* xa = pipe.buf(st, 0) + off;
+      float* xb = pipe.buf(st, 1) + off;
+#pragma unroll
+      for (int j = 0; j < kE; ++j) { xa[j] = x0[ST ? j : 0] * G[j]; xb[j] = x1[ST ? j : 0] * G[j]; }
+    } else if (!LA) {
       for (int c = 0; c < C; ++c) {
         float* xb = pipe.buf(st, c) + off;
 #pragma unroll
@@ -332,7 +349,7 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
 }
 
 // =============================================================================== backward
-template <Curve CV, int W, bool LA>
+template <Curve CV, int W, bool LA, bool ST = false>
 __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<W> sm(smem_raw);
@@ -371,12 +388,25 @@ __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
 
     // ---- recompute the forward quantities of this tile from its checkpoint ----
     float xs[kE], s[kE], gcv[kE], dxdbv[kE], drv[kE], dwv[kE];   // gain computer value + partials (d/dT = -d/dxdb)
+    float x0[ST ? kE : 1], x1[ST ? kE : 1], g0[ST ? kE : 1], g1[ST ? kE : 1];   // stereo: x and dL/dy stay in registers
+    if (ST) {
+      const float* xa = pipe.buf(st, 0) + off;
+      const float* xb = pipe.buf(st, 1) + off;
+      const float* ga = pipe.buf(st, 2) + off;
+      const float* gb = pipe.buf(st, 3) + off;
 #pragma unroll
-    for (int j = 0; j < kE; ++j) xs[j] = 0.f;
-    for (int c = 0; c < C; ++c) {
-      const float* xb = pipe.buf(st, c) + off;
+      for (int j = 0; j < kE; ++j) {
+        x0[ST ? j : 0] = xa[j]; x1[ST ? j : 0] = xb[j]; g0[ST ? j : 0] = ga[j]; g1[ST ? j : 0] = gb[j];
+        xs[j] = xa[j] + xb[j];
+      }
+    } else {
 #pragma unroll
-      for (int j = 0; j < kE; ++j) xs[j] += xb[j];
+      for (int j = 0; j < kE; ++j) xs[j] = 0.f;
+      for (int c = 0; c < C; ++c) {
+        const float* xb = pipe.buf(st, c) + off;
+#pragma unroll
+        for (int j = 0; j < kE; ++j) xs[j] += xb[j];
+      }
     }
     {
       float run = 0.f;
@@ -399,8 +429,8 @@ __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
     {
       float dG[kE];
 #pragma unroll
-      for (int j = 0; j < kE; ++j) dG[j] = 0.f;
-      for (int c = 0; c < C; ++c) {
+      for (int j = 0; j < kE; ++j) dG[j] = ST ? fmaf(g0[ST ? j : 0], x0[ST ? j : 0], g1[ST ? j : 0] * x1[ST ? j : 0]) : 0.f;
+      for (int c = 0; c < (ST ? 0 : C); ++c) {
         const float* xb = pipe.buf(st, c) + off;
         const float* gb = pipe.buf(st, C + c) + off;
         if (!LA) {
@@ -447,7 +477,12 @@ __global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
       }
       dxs[j] = dx;
     }
-    if (!LA) {
+    if (ST) {
+      float* ga = pipe.buf(st, 2) + off;
+      float* gb = pipe.buf(st, 3) + off;
+#pragma unroll
+      for (int j = 0; j < kE; ++j) { ga[j] = fmaf(g0[ST ? j : 0], G[j], dxs[j]); gb[j] = fmaf(g1[ST ? j : 0], G[j], dxs[j]); }
+    } else if (!LA) {
       for (int c = 0; c < C; ++c) {
         float* gb = pipe.buf(st, C + c) + off;
 #pragma unroll
@@ -518,6 +553,13 @@ int pick_warps(int64_t bs, int chs, int nbuf_per_ch) {
   while (w > 1 && (size_t)kStages * nbuf_per_ch * chs * (w * 32 * kE) * 4 + kSmemHeader > 96 * 1024) w /= 2;
   return w;
 }
+// experiment / test knob: DASP_DYN_GENERIC=1 disables the stereo specialisation (the generic channel loop is the path
+// every other channel count takes, so the two are compared on the same stereo inputs by the tests)
+int debug_generic_channels() {
+  const char* v = getenv("DASP_DYN_GENERIC");
+  return (v && atoi(v)) ? 1 : 0;
+}
+
 // one-off opt-in to the largest dynamic shared memory any launch of `kernel` may ask for (pick_warps caps it at
 // 96 KB), cached per (host thread, device, kernel instantiation: a non-type template parameter) instead of a driver call on every launch
 template <auto Kernel>
@@ -533,29 +575,33 @@ int ensure_smem_optin() {
 }
 size_t smem_bytes(int w, int nbuf) { return kSmemHeader + (size_t)kStages * nbuf * (w * 32 * kE) * 4; }
 
-template <Curve CV, int W, bool LA>
+template <Curve CV, int W, bool LA, bool ST>
 int launch_fwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
   const size_t smem = smem_bytes(W, p.chs);
-  { int rc = ensure_smem_optin<dynamics_fwd_kernel<CV, W, LA>>(); if (rc != DASP_OK) return rc; }
-  dynamics_fwd_kernel<CV, W, LA><<<(unsigned)bs, W * 32, smem, st>>>(p);
+  { int rc = ensure_smem_optin<dynamics_fwd_kernel<CV, W, LA, ST>>(); if (rc != DASP_OK) return rc; }
+  dynamics_fwd_kernel<CV, W, LA, ST><<<(unsigned)bs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("dynamics_fwd_kernel");
   return DASP_OK;
 }
-template <Curve CV, int W, bool LA>
+template <Curve CV, int W, bool LA, bool ST>
 int launch_bwd_la(const DynParams& p, int64_t bs, cudaStream_t st) {
   const size_t smem = smem_bytes(W, 2 * p.chs);
-  { int rc = ensure_smem_optin<dynamics_bwd_kernel<CV, W, LA>>(); if (rc != DASP_OK) return rc; }
-  dynamics_bwd_kernel<CV, W, LA><<<(unsigned)bs, W * 32, smem, st>>>(p);
+  { int rc = ensure_smem_optin<dynamics_bwd_kernel<CV, W, LA, ST>>(); if (rc != DASP_OK) return rc; }
+  dynamics_bwd_kernel<CV, W, LA, ST><<<(unsigned)bs, W * 32, smem, st>>>(p);
   DASP_LAUNCH_OK("dynamics_bwd_kernel");
   return DASP_OK;
 }
 template <Curve CV, int W>
 int launch_fwd_w(const DynParams& p, int64_t bs, cudaStream_t st) {
-  return p.lookahead > 0 ? launch_fwd_la<CV, W, true>(p, bs, st) : launch_fwd_la<CV, W, false>(p, bs, st);
+  if (p.lookahead > 0) return launch_fwd_la<CV, W, true, false>(p, bs, st);
+  return (p.chs == 2 && !debug_generic_channels()) ? launch_fwd_la<CV, W, false, true>(p, bs, st)
+                                                   : launch_fwd_la<CV, W, false, false>(p, bs, st);
 }
 template <Curve CV, int W>
 int launch_bwd_w(const DynParams& p, int64_t bs, cudaStream_t st) {
-  return p.lookahead > 0 ? launch_bwd_la<CV, W, true>(p, bs, st) : launch_bwd_la<CV, W, false>(p, bs, st);
+  if (p.lookahead > 0) return launch_bwd_la<CV, W, true, false>(p, bs, st);
+  return (p.chs == 2 && !debug_generic_channels()) ? launch_bwd_la<CV, W, false, true>(p, bs, st)
+                                                   : launch_bwd_la<CV, W, false, false>(p, bs, st);
 }
 
 template <Curve CV>
