@@ -31,7 +31,13 @@ namespace {
 #define DASP_DYN_E 7
 #endif
 constexpr int kE = DASP_DYN_E;        // samples per thread per tile; odd => stride-E smem access is conflict-free
-constexpr int kStages = 3;
+#ifndef DASP_DYN_STAGES
+#define DASP_DYN_STAGES 3
+#endif
+#ifndef DASP_DYN_BWD_MINB
+#define DASP_DYN_BWD_MINB 4      // resident CTAs per SM the backward is compiled for at W = 4 (register budget 65536 / (128 * MINB))
+#endif
+constexpr int kStages = DASP_DYN_STAGES;
 constexpr int kMaxChs = 32;
 constexpr float kDbPerLog2 = 6.020599913279624f;    // 20*log10(2)
 constexpr float kDbGradScale = 8.685889638065035f;  // 20/ln(10)
@@ -350,7 +356,7 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
 
 // =============================================================================== backward
 template <Curve CV, int W, bool LA, bool ST = false>
-__global__ void __launch_bounds__(W * 32) dynamics_bwd_kernel(DynParams p) {
+__global__ void __launch_bounds__(W * 32, (W <= 4) ? (4 * DASP_DYN_BWD_MINB) / W : 2) dynamics_bwd_kernel(DynParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<W> sm(smem_raw);
   __shared__ float red[5][W];
