@@ -681,6 +681,35 @@ def main():
                          "ms_per_step": round(ms2 / n2, 4), "value": items2 * CHS * N_SAMPLES * n2 / (ms2 * 1e-3)}
         del st2
         torch.cuda.empty_cache()
+        # ---- (c) BASELINE config 4 ("reverb 256 stereo, IR 96000, 1 -> 4 GPU"): the 256 items split over the ranks ----
+        b4 = ddist.shard_sizes(256, world)[rank]
+        g4 = torch.Generator().manual_seed(7 + rank)
+        x4 = (torch.rand(max(b4, 1), CHS, N_SAMPLES, generator=g4) * 2 - 1).to(dev).requires_grad_(True)
+        p4 = [torch.rand(max(b4, 1), generator=g4).to(dev).requires_grad_(True) for _ in range(25)]
+        gy4 = torch.rand(max(b4, 1), CHS, N_SAMPLES, device=dev)
+        flush4 = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def c4_step():
+            D.noise_shaped_reverberation(x4, SR, *p4, num_samples=IR_LEN, num_bandpass_taps=TAPS).backward(gy4)
+            x4.grad = None
+
+        for _ in range(2):
+            c4_step()
+        ts4 = []
+        for _ in range(5):
+            flush4.zero_()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); c4_step(); b.record()
+            barrier()
+            ts4.append(max_over_ranks(a.elapsed_time(b)))
+        ms4 = statistics.median(ts4)
+        extras["c4_reverb_256x2x48000_ir96000_sharded"] = {
+            "items_per_gpu": ddist.shard_sizes(256, world), "fwdbwd_ms": round(ms4, 4),
+            "gsamples_per_s": round(256 * CHS * N_SAMPLES / ms4 / 1e6, 2),
+            "note": "eager fwd+bwd of the 256-item batch split over the ranks, device-timed, max over ranks, L2 flushed"}
+        del x4, p4, gy4, flush4
+        torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()

@@ -486,7 +486,12 @@ __global__ void __launch_bounds__(W * 32) eq_fwd_kernel(EqParams p) {
   using SM = Smem<C, W, S, S>;
   SM sm(smem_raw);
   const Tables<C>& tb = *sm.tb;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // the warp index, read from lane 0: the compiler then KNOWS it is warp-uniform.  With `threadIdx.x >> 5` the
+  // warp-strided tile loop below counts as divergent and every shuffle of the scans is emitted as a five-instruction
+  // WARPSYNC.COLLECTIVE / MOV / SHFL / MOV / ENDCOLLECTIVE sequence through two fixed registers (measured on the SASS:
+  // 1776 SHFL + 1804 collective brackets + ~2300 extra MOV in eq_bwd_kernel, and no overlap between shuffles).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const PairRows pr = pair_rows(blockIdx.x, p.rows);
 
   build_tables(*sm.tb, p.params, pr.row_a / p.chs, pr.row_b / p.chs, p.sample_rate);
@@ -569,7 +574,12 @@ __global__ void __launch_bounds__(W * 32) eq_bwd_kernel(EqParams p) {
   SM sm(smem_raw);
   const Tables<C>& tb = *sm.tb;
   __shared__ double red[W][kSections * 5][2];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // the warp index, read from lane 0: the compiler then KNOWS it is warp-uniform.  With `threadIdx.x >> 5` the
+  // warp-strided tile loop below counts as divergent and every shuffle of the scans is emitted as a five-instruction
+  // WARPSYNC.COLLECTIVE / MOV / SHFL / MOV / ENDCOLLECTIVE sequence through two fixed registers (measured on the SASS:
+  // 1776 SHFL + 1804 collective brackets + ~2300 extra MOV in eq_bwd_kernel, and no overlap between shuffles).
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const PairRows pr = pair_rows(blockIdx.x, p.rows);
   const int64_t row_a = pr.row_a, row_b = pr.row_b;
   const bool has_b = pr.has_b;
