@@ -51,6 +51,16 @@ def main():
             out.append("BASELINE configs 2-4 on one GPU (device-timed, L2 flushed): " + "; ".join(
                 f"`{k}` fwd {v['fwd_ms']:.3f} ms, fwd+bwd {v['fwdbwd_ms']:.3f} ms ({v['gsamples_per_s']:.1f} G samples/s)"
                 for k, v in cfg.items()) + ".")
+        sh = []
+        for n in (2, 4, 8):
+            d = load(n)
+            c4 = (d or {}).get("c4_reverb_256x2x48000_ir96000_sharded")
+            if c4:
+                sh.append(f"{n} GPUs ({c4['items_per_gpu'][0]} items each) {c4['fwdbwd_ms']:.3f} ms = {c4['gsamples_per_s']:.1f} G samples/s")
+        if sh and "c4_reverb_256x2x48000_ir96000" in cfg:
+            out.append("")
+            out.append(f"Config 4 (reverb 256 x 2 x 48000, IR 96000) split over the GPUs, fwd+bwd: 1 GPU "
+                       f"{cfg['c4_reverb_256x2x48000_ir96000']['fwdbwd_ms']:.3f} ms; " + "; ".join(sh) + ".")
         rg, cb = d1.get("reference_gpu"), d1.get("cpu_baseline")
         if rg and "value" in rg:
             out.append("")
@@ -61,5 +71,24 @@ def main():
     print("\n".join(out))
 
 
+def update_readme():
+    """replace the block between the results markers of README.md"""
+    import io
+    import contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        main()
+    path = os.path.join(ROOT, "README.md")
+    text = open(path).read()
+    a = text.index("<!-- results:begin")
+    a = text.index("\n", a) + 1
+    b = text.index("<!-- results:end -->")
+    head = "### Measured on B200 (round 2; `profiles/r02_bench_n{1,2,4,8}.json`, all four from the final build)\n\n"
+    open(path, "w").write(text[:a] + head + buf.getvalue() + text[b:])
+
+
 if __name__ == "__main__":
-    main()
+    if "--update-readme" in sys.argv:
+        update_readme()
+    else:
+        main()
