@@ -754,6 +754,20 @@ def main():
                         "traffic_source": traffic_src if dom in traffic_item else None, "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": breakdown[dom]["ms"],
                         "note": "stage = one C-ABI call, timed with CUDA events around it in an eager pass of the same step"}
+        if roofline and dom in ("reverb_fwd", "reverb_bwd"):
+            # context, not the roofline: the reverb is transform work, not streaming.  Transforms per item (8192-point
+            # complex, 5 n log2 n flops): forward 12 bands x R classes (IR synthesis) + J (IR partitions) + 2 I (audio in,
+            # wet out); backward I (dL/dy) + I (dL/dx) + J (dL/dIR).  Peak = SMs x 128 lanes x 2 x max SM clock.
+            R = -(-(leff + TAPS - 1) // 8192); I = -(-N_SAMPLES // 4096); J = -(-leff // 4096)
+            nfft = (12 * R + J + 2 * I) if dom == "reverb_fwd" else (2 * I + J)
+            flops = nfft * 5 * 8192 * 13 * bs
+            props = torch.cuda.get_device_properties(dev)
+            fp32_peak = props.multi_processor_count * 128 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12
+            roofline["fft_context"] = {
+                "transforms_per_item": nfft, "fft_TFLOPs": round(flops / (breakdown[dom]["ms"] * 1e-3) / 1e12, 2),
+                "fp32_peak_TFLOPs": round(fp32_peak, 1),
+                "frac_of_fp32_peak": round(flops / (breakdown[dom]["ms"] * 1e-3) / 1e12 / fp32_peak, 3),
+                "note": "5 n log2 n flops of the 8192-point transforms only (generator, MACs, shaping not counted)"}
         chunk_items = F.reverb_chunk_items(dev)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
