@@ -65,7 +65,7 @@ int dasp_abi_version(void) { return DASP_ABI_VERSION; }
 const char* dasp_last_error(void) { return dasp::g_err; }
 int dasp_compiled_arch(void) { return 1000; }
 void dasp_shutdown(void) { dasp::reverb_shutdown(); }
-void dasp_debug_force_warps(int warps) { dasp::g_forced_warps = (warps == 1 || warps == 2 || warps == 3 || warps == 4 || warps == 8) ? warps : 0; }
+void dasp_debug_force_warps(int warps) { dasp::g_forced_warps = (warps == 1 || warps == 2 || warps == 3 || warps == 4 || warps == 8 || warps == 16) ? warps : 0; }
 
 int dasp_denormalize(const float* p01, const float* lo, const float* span, float* out, int* flag, int64_t rows,
                      int64_t cols, void* stream) {

@@ -834,14 +834,18 @@ int tune_bwd_s() {
 // force the general (pair-coefficient) tables even when every pair lies inside one item: test hook via the env
 int tune_force_pair_tables() { static const int v = env_int("DASP_EQ_PAIR_TABLES"); return v; }
 
-// Warps per row pair (W in {1, 2, 3, 4, 8}; 0 / other = automatic).  Measured on B200 at 1024 pairs x 48000 samples
+// Warps per row pair (W in {1, 2, 3, 4, 8}, forward also 16; 0 / other = automatic).  Measured on B200 at 1024 pairs x 48000 samples
 // (profiles/r02_eq_variants.md): forward W=4 with two load stages beats W=2 and the single-wave choices; small batches
 // want W=8 to fill the SMs at all.  The backward holds 255 registers per thread, i.e. 8 warps per SM whatever the
 // split: W=8 with one stage (one CTA per SM, least shared memory per warp) measured best.
 bool valid_w(int w) { return w == 1 || w == 2 || w == 3 || w == 4 || w == 8; }
+// The forward also has W = 16 (512 threads, 80 registers): when there is at most one row pair per SM (e.g. 1024 stereo
+// items split over 8 GPUs) a pair's CTA is alone on its SM, and sixteen warps walk its tiles twice as fast as eight.
+// The backward cannot follow (255 registers per thread x 512 threads exceed the register file).
 int pick_fwd_warps(int64_t pairs, int tuned) {
   const int f = debug_forced_warps() ? debug_forced_warps() : tuned;
-  if (valid_w(f)) return f;
+  if (valid_w(f) || f == 16) return f;
+  if (pairs <= sm_count()) return 16;
   return (pairs * 4 < 20ll * sm_count()) ? 8 : 4;
 }
 int pick_bwd_warps(int tuned) {
@@ -899,6 +903,7 @@ int dispatch_fwd(int w, const EqParams& p, int64_t pairs, cudaStream_t st) {
     case 2: return launch_fwd<C, 2, S>(p, pairs, st);
     case 3: return launch_fwd<C, 3, S>(p, pairs, st);
     case 4: return launch_fwd<C, 4, S>(p, pairs, st);
+    case 16: return launch_fwd<C, 16, S>(p, pairs, st);
     default: return launch_fwd<C, 8, S>(p, pairs, st);
   }
 }

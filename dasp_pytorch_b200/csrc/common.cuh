@@ -55,7 +55,8 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
-// Test hook (dasp_debug_force_warps): 0 = automatic; 1/2/4/8 pins the warps-per-row choice of the scan kernels
+// Test hook (dasp_debug_force_warps): 0 = automatic; 1/2/3/4/8/16 pins the warps-per-row choice of the scan kernels
+// (a kernel family that has no such variant keeps its automatic choice)
 // so that every kernel variant can be exercised at small, cheap-to-check batch sizes.
 int debug_forced_warps();
 // Test hook (dasp_debug_eq_bwd_stages): 0 = automatic; 1 / 2 pins the number of x / dL/dy stages of the EQ backward

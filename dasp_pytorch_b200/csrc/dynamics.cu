@@ -248,17 +248,17 @@ __device__ __forceinline__ CurveOut gain_computer(float xdb, const CurveK& k) {
 // i.e. < 1e-5 dB here) -- the accurate log2f costs ~15 instructions in a kernel that is issue bound
 __device__ __forceinline__ float level_db(float xs, float eps) { return kDbPerLog2 * __log2f(fmaxf(fabsf(xs), eps)); }
 
-// shared-memory carve-up (dynamic smem): [S mbarriers][pad to 128][agg: 2*W floats][pad][stages]
+// shared-memory carve-up (dynamic smem): [S mbarriers][pad to 64][agg: 4*W floats][pad to 512][stages]
 template <int W>
 struct Smem {
   uint64_t* bars; float* agg; float* stages;
   __device__ __forceinline__ Smem(unsigned char* base) {
     bars = reinterpret_cast<uint64_t*>(base);
-    agg = reinterpret_cast<float*>(base + 64);
-    stages = reinterpret_cast<float*>(base + 256);
+    agg = reinterpret_cast<float*>(base + 64);        // up to 4 * 16 floats (backward, W = 16)
+    stages = reinterpret_cast<float*>(base + 512);
   }
 };
-constexpr size_t kSmemHeader = 256;
+constexpr size_t kSmemHeader = 512;
 
 // =============================================================================== forward
 // LA: lookahead_samples > 0 (rare; kept out of the common instantiation).  ST: stereo specialisation (C == 2, no
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(W * 32) dynamics_fwd_kernel(DynParams p) {
 
 // =============================================================================== backward
 template <Curve CV, int W, bool LA, bool ST = false>
-__global__ void __launch_bounds__(W * 32, (W <= 4) ? (4 * DASP_DYN_BWD_MINB) / W : 2) dynamics_bwd_kernel(DynParams p) {
+__global__ void __launch_bounds__(W * 32, (W <= 4) ? (4 * DASP_DYN_BWD_MINB) / W : (W == 8 ? 2 : 1)) dynamics_bwd_kernel(DynParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   Smem<W> sm(smem_raw);
   __shared__ float red[5][W];
@@ -550,13 +550,22 @@ __global__ void dynamics_lookahead_fixup_kernel(const float* __restrict__ gy, co
 }
 
 // ---- host side -----------------------------------------------------------------------------
+// shared memory a CTA of w warps may ask for: 96 KB (two or more CTAs per SM) up to 8 warps, 200 KB for the one-CTA-per-SM
+// geometry W = 16
+constexpr size_t kSmemLimit = 96 * 1024, kSmemLimit16 = 200 * 1024;
 int pick_warps(int64_t bs, int chs, int nbuf_per_ch) {
   // enough warps to fill the chip, limited by shared memory (S stages * nbuf * tile bytes)
   const int64_t want = 16ll * sm_count();
   int w = 1;
   while (w < 8 && bs * w < want) w *= 2;
-  { const int f = debug_forced_warps(); if (f == 1 || f == 2 || f == 4 || f == 8) w = f; }
-  while (w > 1 && (size_t)kStages * nbuf_per_ch * chs * (w * 32 * kE) * 4 + kSmemHeader > 96 * 1024) w /= 2;
+  // small batches (at most one item per SM: e.g. 1024 items split over 8 GPUs): one 16-warp CTA per item, so that an SM
+  // still runs 16 warps; the item's tiles are walked serially, and a 16-warp tile halves their number
+  if (w == 8 && bs <= sm_count()) w = 16;
+  { const int f = debug_forced_warps(); if (f == 1 || f == 2 || f == 4 || f == 8 || f == 16) w = f; }
+  auto fits = [&](int ww) {
+    return (size_t)kStages * nbuf_per_ch * chs * (ww * 32 * kE) * 4 + kSmemHeader <= (ww == 16 ? kSmemLimit16 : kSmemLimit);
+  };
+  while (w > 1 && !fits(w)) w /= 2;
   return w;
 }
 // experiment / test knob: DASP_DYN_GENERIC=1 disables the stereo specialisation (the generic channel loop is the path
@@ -567,14 +576,14 @@ int debug_generic_channels() {
 }
 
 // one-off opt-in to the largest dynamic shared memory any launch of `kernel` may ask for (pick_warps caps it at
-// 96 KB), cached per (host thread, device, kernel instantiation: a non-type template parameter) instead of a driver call on every launch
+// 96 KB / 200 KB), cached per (host thread, device, kernel instantiation: a non-type template parameter) instead of a driver call on every launch
 template <auto Kernel>
 int ensure_smem_optin() {
   static thread_local int done_dev = -1;
   int dev = 0;
   DASP_CUDA_OK(cudaGetDevice(&dev));
   if (done_dev != dev) {
-    DASP_CUDA_OK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024 + 256));
+    DASP_CUDA_OK(cudaFuncSetAttribute(Kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit16));
     done_dev = dev;
   }
   return DASP_OK;
@@ -616,6 +625,7 @@ int dispatch(bool bwd, int w, const DynParams& p, int64_t bs, cudaStream_t st) {
     case 1: return bwd ? launch_bwd_w<CV, 1>(p, bs, st) : launch_fwd_w<CV, 1>(p, bs, st);
     case 2: return bwd ? launch_bwd_w<CV, 2>(p, bs, st) : launch_fwd_w<CV, 2>(p, bs, st);
     case 4: return bwd ? launch_bwd_w<CV, 4>(p, bs, st) : launch_fwd_w<CV, 4>(p, bs, st);
+    case 16: return bwd ? launch_bwd_w<CV, 16>(p, bs, st) : launch_fwd_w<CV, 16>(p, bs, st);
     default: return bwd ? launch_bwd_w<CV, 8>(p, bs, st) : launch_fwd_w<CV, 8>(p, bs, st);
   }
 }

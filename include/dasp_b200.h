@@ -45,7 +45,8 @@ int dasp_compiled_arch(void);
 void dasp_shutdown(void);
 /* The dasp_debug_* entry points are TEST HOOKS: process-global switches, not thread-safe, not for production
  * callers (they exist so that every kernel variant can be pinned against the oracle at small sizes). */
-/* test hook: pin the warps-per-row variant of the scan kernels (1, 2, 4, 8; 0 = automatic choice) */
+/* test hook: pin the warps-per-row variant of the scan kernels (1, 2, 3, 4, 8, 16; 0 = automatic choice; a kernel
+ * family without the requested variant keeps its automatic choice) */
 void dasp_debug_force_warps(int warps);
 /* test hook: pin the number of x / dL/dy stages per warp of the EQ backward (1 or 2; 0 = automatic) */
 void dasp_debug_eq_bwd_stages(int stages);

@@ -84,7 +84,7 @@ def test_compressor_ragged_shapes(cuda_device, bs, chs, n):
     _ragged_check(cuda_device, bs, chs, n, seed=6)
 
 
-@pytest.mark.parametrize("warps", [1, 2, 4, 8])
+@pytest.mark.parametrize("warps", [1, 2, 4, 8, 16])
 def test_compressor_every_warps_per_item_variant(cuda_device, warps):
     """pin each warps-per-item kernel variant (test hook) on a small batch with several tiles + a ragged tail"""
     from dasp_pytorch_b200 import _abi

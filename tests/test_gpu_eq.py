@@ -71,7 +71,7 @@ def test_eq_ragged_shapes(cuda_device, bs, chs, n):
     _check(cuda_device, x, denorm(p01, eq_ranges()), tail=1 << 16)
 
 
-@pytest.mark.parametrize("warps,stages", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (4, 1), (4, 2), (8, 1)])
+@pytest.mark.parametrize("warps,stages", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 1), (3, 2), (4, 1), (4, 2), (8, 1), (16, 1), (16, 2)])
 def test_eq_every_warps_per_pair_variant(cuda_device, warps, stages):
     """the kernels pick 1/2/4/8 warps per row pair from the batch size (warp w owns tiles w, w+W, ...; carries travel
     through mbarrier-guarded mailboxes) and 1 or 2 load stages in the backward; pin each variant (test hooks) on a
@@ -97,7 +97,7 @@ def test_eq_is_deterministic_and_warp_count_invariant(cuda_device):
     xs = x.to(cuda_device)
     ps = [p.to(cuda_device) for p in denorm(p01, eq_ranges())]
     outs = []
-    for w in (1, 2, 3, 4, 8, 2):
+    for w in (1, 2, 3, 4, 8, 16, 2):          # 16 exists for the forward only (the backward keeps its own choice)
         _abi.lib().dasp_debug_force_warps(w)
         try:
             xx = xs.clone().requires_grad_(True)
