@@ -7,4 +7,3 @@ timeout 600 python bench.py --batch $b --steps 20 --warmup 3 --no-extras 2>/dev/
 import sys, json
 d = json.loads(sys.stdin.read()); print('batch $b ms_per_step=%.4f value=%.4g stages=%s' % (d['ms_per_step'], d['value'], json.dumps({k: v['ms'] for k, v in d['stages'].items()})))"
 done 2>&1 | tee gpurun_out/a21_bench.log
-DASP_DYN_MAXW8=1 true
